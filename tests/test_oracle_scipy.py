@@ -1,4 +1,9 @@
-"""Independent-math cross-checks of the oracle (scipy in f64), SURVEY.md §4 row 2."""
+"""Independent-math cross-checks of the oracle (scipy in f64), SURVEY.md §4 row 2.
+
+These compare the f32 oracle with IDEAL (f64) filters, so the bound is the reference arithmetic's own
+rounding noise, not the GPU parity tolerance: the f32 DirectForm1 high-pass at 200 Hz sits ~1.3e-5 of
+its output peak away from exact math.  That is why the CUDA engine runs recurrences bit-exactly
+(DESIGN.md "IIR exactness") instead of re-ordering them."""
 import numpy as np
 from scipy import signal as sps
 
@@ -8,7 +13,7 @@ from tests.util import NF1, assert_audio_close, make_oracle
 
 
 def test_biquad_cascade_vs_lfilter(oracle_mod):
-    x = S.noise(4, 48000 // 4)
+    x = S.noise(4, 12032)
     o = make_oracle(oracle_mod, S.config2(), 4)
     y = o.process(x)[0]
     lp, hp = S.rbj_biquad("lp", 1000.0), S.rbj_biquad("hp", 200.0)
@@ -16,7 +21,7 @@ def test_biquad_cascade_vs_lfilter(oracle_mod):
     v = x.astype(np.float64) / nf
     v = sps.lfilter([lp["b0"], lp["b1"], lp["b2"]], [1.0, lp["a1"], lp["a2"]], v, axis=1) / nf
     v = sps.lfilter([hp["b0"], hp["b1"], hp["b2"]], [1.0, hp["a1"], hp["a2"]], v, axis=1) / nf
-    assert_audio_close(y, v, what="oracle biquad cascade vs scipy f64")
+    assert_audio_close(y, v, rel_tol=1e-4, what="oracle biquad cascade vs scipy f64")
 
 
 def test_one_pole_vs_lfilter(oracle_mod):
