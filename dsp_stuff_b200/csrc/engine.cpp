@@ -1,0 +1,1241 @@
+// engine.cpp — host side of the B200 batch engine: node registry, graph model, topological
+// scheduler that lowers the graph to fused device programs + FIR steps, state/ring/FIR memory, and
+// the C ABI declared in include/dspb200.h.
+//
+// Replaces (reference paths relative to dsp-stuff/src):
+//   nodes/mod.rs:65-123 (type registry)            -> kNodeTypes
+//   dsp-stuff-derive/src/lib.rs:163-231 (defaults, port order) -> NodeType tables
+//   runtime.rs:125-224, 646-732 (links, per-port link vectors, task loops) -> Engine::compile / process
+//   node.rs:162-194, 267-352 (fan-in average, per-block wrapper) -> lowering in Lowerer
+// There is no CPU execution path in this file: every dspb_process ends in CUDA launches.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/dspb200.h"
+#include "json_min.h"
+#include "plan.h"
+
+using namespace dspb;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) return fail(DSPB_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+// ---- node registry: verbatim mirror of the #[dsp(...)] blocks -------------------
+enum TypeId { T_GAIN, T_DISTORT, T_OVERDRIVE, T_CHEBY, T_BIQUAD, T_LOWPASS, T_HIGHPASS, T_REVERB, T_FIR,
+              T_ADD, T_MIX, T_MUX, T_DEMUX, T_ENVELOPE, T_SIGGEN, T_INPUT, T_OUTPUT, T_COUNT };
+
+struct ParamDef {
+    const char* name;
+    float def, lo, hi;
+    int ctl_port;  // input-port index of the same-named control port (slider(as_input)), -1 if none
+};
+struct EnumDef {
+    const char* name;
+    std::vector<const char*> variants;
+    int def;
+};
+struct NodeType {
+    const char* cfg_name;
+    std::vector<const char*> ins, outs;
+    std::vector<ParamDef> params;
+    std::vector<EnumDef> enums;
+};
+
+const NodeType kNodeTypes[T_COUNT] = {
+    /* gain       nodes/gain.rs:5-23      */ {"gain", {"in", "level"}, {"out"}, {{"level", 1.0f, 0.f, 10.f, 1}}, {}},
+    /* distort    nodes/distort.rs:18-51  */
+    {"distort", {"in", "level"}, {"out"}, {{"level", 0.0f, 0.f, 30.f, 1}},
+     {{"mode", {"HardClip", "SoftClip", "Tanh", "RecipSoftClip", "Fuzz", "Sin", "Atan", "Square", "Chebyshev4"}, 1}}},
+    /* overdrive  nodes/overdrive.rs:5-29 */
+    {"overdrive", {"in", "boost", "drive", "level"}, {"out"},
+     {{"boost", 0.f, 0.f, 30.f, 1}, {"drive", 0.f, 0.f, 1.f, 2}, {"level", 0.f, 0.f, 1.f, 3}}, {}},
+    /* chebyshev  nodes/chebyshev.rs:5-26 */
+    {"chebyshev", {"in"}, {"out"}, {{"level_pos", 0.f, 0.f, 50.f, -1}, {"level_neg", 0.f, 0.f, 50.f, -1}}, {}},
+    /* biquad     nodes/biquad.rs:8-45    */
+    {"biquad", {"in"}, {"out"},
+     {{"a0", 1.0f, -10.f, 10.f, -1}, {"a1", -0.24f, -10.f, 10.f, -1}, {"a2", 0.f, -10.f, 10.f, -1},
+      {"b0", 0.758f, -10.f, 10.f, -1}, {"b1", 0.f, -10.f, 10.f, -1}, {"b2", 0.f, -10.f, 10.f, -1}}, {}},
+    /* low_pass   nodes/low_pass.rs:4-24 (its cfg_name() says "high_pass"; RESTORE key is low_pass) */
+    {"low_pass", {"in"}, {"out"}, {{"ratio", 0.5f, 0.f, 1.f, -1}}, {}},
+    /* high_pass  nodes/high_pass.rs:4-24 */ {"high_pass", {"in"}, {"out"}, {{"ratio", 0.5f, 0.f, 1.f, -1}}, {}},
+    /* reverb     nodes/reverb.rs:12-42   */
+    {"reverb", {"in"}, {"out"}, {{"seconds", 0.5f, 0.f, 1.f, -1}, {"decay", 0.5f, 0.f, 1.f, -1}}, {}},
+    /* fir        nodes/fir.rs:19-66      */ {"fir", {"in"}, {"out"}, {}, {{"mode", {"Average", "Balanced"}, 1}}},
+    /* add        nodes/add.rs:4-20       */ {"add", {"a", "b"}, {"out"}, {}, {}},
+    /* mix        nodes/mix.rs:5-29       */ {"mix", {"a", "b", "ratio"}, {"out"}, {{"ratio", 0.5f, 0.f, 1.f, 2}}, {}},
+    /* mux        nodes/mux.rs:5-41       */ {"mux", {"a", "b"}, {"out"}, {}, {{"in_port", {"A", "B"}, 0}}},
+    /* demux      nodes/demux.rs:5-41     */ {"demux", {"in"}, {"a", "b"}, {}, {{"out_port", {"A", "B"}, 0}}},
+    /* envelope   nodes/envelope.rs:9-32  */
+    {"envelope", {"in"}, {"out"}, {{"attack", 0.f, 0.f, 1000.f, -1}, {"release", 0.f, 0.f, 1000.f, -1}}, {}},
+    /* signal_gen nodes/signal_gen.rs:6-53 */
+    {"signal_gen", {"amplitude", "frequency"}, {"out"},
+     {{"amplitude", 0.5f, -1.f, 1.f, 0}, {"frequency", 100.0f, 0.1f, 20000.f, 1}},
+     {{"mode", {"Sine", "Triangle", "Square", "Constant"}, 0}}},
+    /* input      nodes/input.rs:12-22    */ {"input", {}, {"out"}, {}, {}},
+    /* output     nodes/output.rs:12-22   */ {"output", {"in"}, {}, {}, {}},
+};
+
+bool g_plan_only = false;  // device == -1: build and describe schedules only; nothing can run
+
+struct DevBuf {  // owning device allocation
+    float* p = nullptr;
+    size_t bytes = 0;
+    bool fake = false;
+    ~DevBuf() { if (p && !fake) cudaFree(p); }
+    int alloc(size_t n_bytes, bool zero) {
+        if (p && !fake) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        if (n_bytes == 0) return DSPB_OK;
+        if (g_plan_only) { fake = true; p = reinterpret_cast<float*>(uintptr_t(16)); bytes = n_bytes; return DSPB_OK; }
+        cudaError_t e = cudaMalloc(&p, n_bytes);
+        if (e != cudaSuccess) { p = nullptr; return fail(DSPB_ERR_NOMEM, "cudaMalloc(%zu): %s", n_bytes, cudaGetErrorString(e)); }
+        bytes = n_bytes;
+        if (zero) {
+            e = cudaMemset(p, 0, n_bytes);
+            if (e != cudaSuccess) return fail(DSPB_ERR_CUDA, "cudaMemset: %s", cudaGetErrorString(e));
+        }
+        return DSPB_OK;
+    }
+};
+
+struct Node {
+    int64_t id;
+    int type;
+    std::vector<float> f32;   // by ParamDef index
+    std::vector<int> enums;   // by EnumDef index
+    // biquad: normalised coefficients (regenerate_filter, nodes/biquad.rs:62-76)
+    float bq[5] = {0.758f, 0.f, 0.f, -0.24f, 0.f};  // b0 b1 b2 a1 a2 (initial_filter, biquad.rs:48-55)
+    // reverb
+    int64_t D = 0, pos = 0;
+    DevBuf ring;
+    bool ring_dirty = true;
+    // stateful recurrences
+    DevBuf state;  // [C x 4] f32
+    // fir
+    std::vector<double> taps{1.0};  // reversed, nodes/fir.rs:61
+    DevBuf U[2];                    // [C x (hist_pad + max_samples)] input incl. history, double-buffered
+    DevBuf Y;                       // [C x max_samples]
+    DevBuf H, taps_dev;
+    int hist_pad = 0, cur_u = 0;
+    int64_t started = 0;            // samples this node has consumed since reset
+    bool fir_dirty = true;
+};
+
+struct Link { int src, sport, dst, dport; };
+
+enum StepKind { STEP_FUSED, STEP_FIR };
+struct Step {
+    StepKind kind;
+    Program prog;   // STEP_FUSED
+    int G = 1;
+    int fir_node = -1;
+    // which prog.bufs entries are rebound per call: ext input terminal t (>=0), ext output terminal t, scratch, fir U/Y
+    struct Bind { int kind; int idx; };  // kind 0 ext-in, 1 ext-out, 2 scratch, 3 fir U (idx=node), 4 fir Y (idx=node)
+    std::vector<Bind> binds;             // parallel to prog.bufs
+    std::vector<int> ring_nodes;         // parallel to prog.rings
+    std::string text;                    // human-readable listing
+};
+
+}  // namespace
+
+struct dspb_engine {
+    dspb_config cfg{};
+    std::vector<std::unique_ptr<Node>> nodes;
+    std::vector<Link> links;
+    bool compiled = false;
+    bool lowered = false;
+    std::vector<int> order, in_terms, out_terms;
+    std::vector<std::vector<std::vector<int>>> in_links, out_links;
+    std::vector<Step> steps;
+    std::vector<std::unique_ptr<DevBuf>> scratch;  // [C x max_samples] intermediates crossing steps
+    // host-memory mode staging
+    std::vector<std::unique_ptr<DevBuf>> h_in, h_out;
+    cudaStream_t s_h2d = nullptr, s_cmp = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> ev_pool;
+    int64_t last_launches = 0;
+    int force_G = 0;
+    bool plan_only = false;
+
+    int find(int64_t id) const {
+        for (size_t i = 0; i < nodes.size(); i++)
+            if (nodes[i]->id == id) return (int)i;
+        return -1;
+    }
+    ~dspb_engine() {
+        for (auto e : ev_pool) cudaEventDestroy(e);
+        if (s_h2d) cudaStreamDestroy(s_h2d);
+        if (s_cmp) cudaStreamDestroy(s_cmp);
+        if (s_d2h) cudaStreamDestroy(s_d2h);
+    }
+};
+
+namespace {
+
+int param_index(const NodeType& nt, const char* name) {
+    for (size_t i = 0; i < nt.params.size(); i++)
+        if (!strcmp(nt.params[i].name, name)) return (int)i;
+    return -1;
+}
+int port_index(const std::vector<const char*>& v, const char* name) {
+    for (size_t i = 0; i < v.size(); i++)
+        if (!strcmp(v[i], name)) return (int)i;
+    return -1;
+}
+
+int64_t round_up(int64_t n, int64_t g) { return g <= 1 ? n : (n + g - 1) / g * g; }
+
+// Reverb::refresh_seconds, nodes/reverb.rs:55-71.  Integer work: must match the reference exactly.
+int64_t reverb_delay(float seconds, int sample_rate, int granule) {
+    float prod = seconds * (float)sample_rate;
+    int64_t num = 0;  // `as usize`: NaN/negative -> 0, truncating, saturating
+    if (prod > 0.0f) num = prod >= 9.0e18f ? (INT64_MAX / 2) : (int64_t)prod;
+    num = std::max<int64_t>(num, 128);
+    return round_up(num, granule);
+}
+
+void biquad_regenerate(Node& n) {  // BiQuad::regenerate_filter, nodes/biquad.rs:62-76 (f32 divisions)
+    const float a0 = n.f32[0];
+    n.bq[3] = n.f32[1] / a0;  // a1
+    n.bq[4] = n.f32[2] / a0;  // a2
+    n.bq[0] = n.f32[3] / a0;  // b0
+    n.bq[1] = n.f32[4] / a0;  // b1
+    n.bq[2] = n.f32[5] / a0;  // b2
+}
+
+bool is_stateful(int type) {
+    return type == T_BIQUAD || type == T_LOWPASS || type == T_HIGHPASS || type == T_ENVELOPE || type == T_SIGGEN;
+}
+
+int clear_node_state(dspb_engine* e, Node& n) {
+    if (n.state.p) CUDA_TRY(cudaMemset(n.state.p, 0, n.state.bytes));
+    if (n.ring.p) CUDA_TRY(cudaMemset(n.ring.p, 0, n.ring.bytes));
+    n.pos = 0;
+    for (auto& u : n.U)
+        if (u.p) CUDA_TRY(cudaMemset(u.p, 0, u.bytes));
+    n.started = 0;
+    n.cur_u = 0;
+    (void)e;
+    return DSPB_OK;
+}
+
+// ---- lowering ------------------------------------------------------------------------------------------------
+// A value is what one node output port carries for the current tile.
+struct Value {
+    enum Where { NONE, VREG, GLOBAL, ZERO } where = NONE;
+    int id = -1;      // virtual vreg id or prog buffer kind key
+    int bind_kind = 0, bind_idx = 0;  // for GLOBAL
+    int def_step = -1;
+};
+
+struct Lowerer {
+    dspb_engine& e;
+    std::vector<Step> steps;
+    Step cur{};
+    std::vector<Op> ops;           // ops of the current fused step (virtual vreg ids)
+    std::vector<std::string> txt;
+    int next_vreg = 0;
+    int n_scratch = 0;
+    std::map<std::pair<int, int>, Value> values;  // (node, out port) -> value
+    std::map<std::pair<int, int>, int> use_step;  // last step that uses the value
+    std::vector<int> node_step;                   // step index in which a node's ops are emitted
+    std::string err;
+
+    explicit Lowerer(dspb_engine& en) : e(en) {}
+
+    int buf_slot(int kind, int idx) {
+        for (size_t i = 0; i < cur.binds.size(); i++)
+            if (cur.binds[i].kind == kind && cur.binds[i].idx == idx) return (int)i;
+        if ((int)cur.binds.size() >= kMaxBufs) { err = "segment uses too many global buffers"; return 0; }
+        cur.binds.push_back({kind, idx});
+        return (int)cur.binds.size() - 1;
+    }
+    void emit(Op op, const std::string& s) {
+        if ((int)ops.size() >= kMaxOps - 1) { err = "segment has too many ops"; return; }
+        ops.push_back(op);
+        txt.push_back(s);
+    }
+    static Op mk(uint8_t code) {
+        Op o;
+        memset(&o, 0, sizeof o);
+        o.code = code;
+        return o;
+    }
+    // acc = value (first term: 0.0 + v) or acc += value
+    void emit_term(const Value& v, bool first, const std::string& what) {
+        if (v.where == Value::ZERO || v.where == Value::NONE) {
+            if (first) emit(mk(OP_ZERO), "acc = 0                      ; " + what);
+            return;  // adding +0.0 changes nothing but the sign of a zero
+        }
+        if (v.where == Value::VREG) {
+            Op o = mk(first ? OP_LOADV : OP_ADDV);
+            o.vreg = (uint8_t)v.id;
+            emit(o, std::string(first ? "acc = 0.0 + v" : "acc += v") + std::to_string(v.id) + "           ; " + what);
+        } else {
+            Op o = mk(first ? OP_LOADG : OP_ADDG);
+            o.buf = (uint8_t)buf_slot(v.bind_kind, v.bind_idx);
+            emit(o, std::string(first ? "acc = 0.0 + G" : "acc += G") + std::to_string(o.buf) + "           ; " + what);
+        }
+    }
+    // collect_and_average (node.rs:162-194) for input port p of node ni; result in acc.
+    bool emit_avg(int ni, int p) {
+        const auto& ls = e.in_links[ni][p];
+        if (ls.empty()) {
+            emit(mk(OP_ZERO), "acc = 0                      ; unconnected port (0/0.0001)");
+            return false;
+        }
+        float nf = 0.0001f;
+        bool first = true;
+        for (int l : ls) {
+            const Link& k = e.links[l];
+            nf += 1.0f;
+            emit_term(values[{k.src, k.sport}], first,
+                      std::string("link ") + kNodeTypes[e.nodes[k.src]->type].cfg_name + "#" + std::to_string(e.nodes[k.src]->id));
+            first = false;
+        }
+        Op d = mk(OP_DIVC);
+        d.p[0] = nf;
+        char b[96];
+        snprintf(b, sizeof b, "acc /= %.9g           ; fan-in average of %zu link(s)", nf, ls.size());
+        emit(d, b);
+        return true;
+    }
+    Value save_value(int ni, int port) {
+        Value v;
+        auto key = std::make_pair(ni, port);
+        const int us = use_step.count(key) ? use_step[key] : -1;
+        v.def_step = (int)steps.size();
+        if (us < 0) { v.where = Value::NONE; return v; }  // never used
+        if (us != v.def_step) {  // crosses a step boundary: global scratch
+            v.where = Value::GLOBAL;
+            v.bind_kind = 2;
+            v.bind_idx = n_scratch++;
+            Op o = mk(OP_STOREG);
+            o.buf = (uint8_t)buf_slot(2, v.bind_idx);
+            emit(o, "G" + std::to_string(o.buf) + " = acc                    ; scratch (crosses a step)");
+        } else {
+            v.where = Value::VREG;
+            v.id = next_vreg++;
+            Op o = mk(OP_SAVEV);
+            o.vreg = (uint8_t)v.id;
+            emit(o, "v" + std::to_string(v.id) + " = acc");
+        }
+        return v;
+    }
+    int temp_save(const std::string& what) {
+        int id = next_vreg++;
+        Op o = mk(OP_SAVEV);
+        o.vreg = (uint8_t)id;
+        emit(o, "v" + std::to_string(id) + " = acc                    ; " + what);
+        return id;
+    }
+    void close_fused();
+    int lower();
+    int finish_vregs(Step& st, std::vector<Op>& o, std::vector<std::string>& t);
+};
+
+// Peephole + vreg allocation for one fused step.  Virtual vregs -> shared-memory slots by liveness.
+int Lowerer::finish_vregs(Step& st, std::vector<Op>& o, std::vector<std::string>& t) {
+    auto reads = [](const Op& op, int v) {
+        if ((op.code == OP_LOADV || op.code == OP_ADDV || op.code == OP_COPYV || op.code == OP_ADD || op.code == OP_MIX) && op.vreg == v) return true;
+        for (int i = 0; i < 3; i++)
+            if ((op.pflags & (1 << i)) && op.pv[i] == v) return true;
+        return false;
+    };
+    // peephole: "vK = acc ; acc = 0.0 + vK" with vK used nowhere else -> "acc = 0.0 + acc"
+    for (size_t i = 0; i + 1 < o.size();) {
+        if (o[i].code == OP_SAVEV && o[i + 1].code == OP_LOADV && o[i + 1].vreg == o[i].vreg) {
+            int v = o[i].vreg, uses = 0;
+            for (size_t k = 0; k < o.size(); k++)
+                if (reads(o[k], v)) uses++;
+            if (uses == 1) {
+                Op z = mk(OP_LOADV);
+                z.vreg = 0xFF;  // acc itself
+                o[i] = z;
+                t[i] = "acc = 0.0 + acc              ; value stays in registers";
+                o.erase(o.begin() + i + 1);
+                t.erase(t.begin() + i + 1);
+                continue;
+            }
+        }
+        i++;
+    }
+    // liveness
+    std::map<int, std::pair<int, int>> live;  // virtual id -> [def, last use]
+    for (size_t i = 0; i < o.size(); i++) {
+        if (o[i].code == OP_SAVEV) {
+            if (!live.count(o[i].vreg)) live[o[i].vreg] = {(int)i, (int)i};
+        }
+        for (auto& kv : live)
+            if (reads(o[i], kv.first)) kv.second.second = (int)i;
+    }
+    std::map<int, int> phys;
+    std::vector<int> slot_free_at;  // op index after which the slot is free
+    for (size_t i = 0; i < o.size(); i++) {
+        if (o[i].code != OP_SAVEV || phys.count(o[i].vreg)) continue;
+        int v = o[i].vreg, s = -1;
+        for (size_t k = 0; k < slot_free_at.size(); k++)
+            if (slot_free_at[k] < (int)i) { s = (int)k; break; }
+        if (s < 0) { slot_free_at.push_back(0); s = (int)slot_free_at.size() - 1; }
+        slot_free_at[s] = live[v].second;
+        phys[v] = s;
+    }
+    for (auto& op : o) {
+        if ((op.code == OP_LOADV || op.code == OP_ADDV || op.code == OP_COPYV || op.code == OP_ADD || op.code == OP_MIX || op.code == OP_SAVEV) && op.vreg != 0xFF)
+            op.vreg = (uint8_t)phys[op.vreg];
+        for (int i = 0; i < 3; i++)
+            if (op.pflags & (1 << i)) op.pv[i] = (uint8_t)phys[op.pv[i]];
+    }
+    st.prog.n_vregs = (int)slot_free_at.size();
+    return DSPB_OK;
+}
+
+void Lowerer::close_fused() {
+    if (ops.empty()) { cur = Step(); txt.clear(); next_vreg = 0; return; }
+    cur.kind = STEP_FUSED;
+    finish_vregs(cur, ops, txt);
+    Program& P = cur.prog;
+    P.n_ops = (int)ops.size();
+    P.needs_tile = 0;
+    int64_t min_ring = INT64_MAX;
+    bool has_rec = false;
+    for (int i = 0; i < P.n_ops; i++) {
+        P.ops[i] = ops[i];
+        const int c = ops[i].code;
+        if (c == OP_BIQUAD || c == OP_LP1 || c == OP_HP1 || c == OP_ENVELOPE) { P.needs_tile = 1; has_rec = true; }
+        if (c == OP_COMB) min_ring = std::min(min_ring, e.nodes[cur.ring_nodes[ops[i].aux & 0xff]]->D);
+    }
+    // Tile geometry: G channels x S = 4096/G samples per CTA.  S may not exceed the shortest comb
+    // delay (a tile must never read a ring slot it writes itself); recurrences run lane = channel,
+    // so they want G large, but the grid wants >= ~1.7 CTAs per SM (148 SMs).
+    const int C = e.cfg.channels;
+    int G = 1;
+    if (has_rec) {
+        G = 32;
+        while (G > 1 && (C + G - 1) / G < 256) G >>= 1;
+    }
+    while ((int64_t)kTile / G > min_ring && G < 32) G <<= 1;
+    if (e.force_G) G = e.force_G;
+    if ((int64_t)kTile / G > min_ring) G = 32;
+    cur.G = G;
+    // cp.async prefetch slots: the first streamed global read, and the first comb ring that allows it
+    const int S = kTile / G;
+    P.n_prefetch = 0;
+    for (int k = 0; k < kMaxPrefetch; k++) P.pf_buf[k] = P.pf_ring[k] = -1;
+    for (int i = 0; i < P.n_ops && P.n_prefetch < 1; i++)
+        if (P.ops[i].code == OP_LOADG) {
+            P.pf_buf[P.n_prefetch] = P.ops[i].buf;
+            P.ops[i].aux = (uint16_t)(++P.n_prefetch);
+        }
+    for (int i = 0; i < P.n_ops && P.n_prefetch < kMaxPrefetch; i++)
+        if (P.ops[i].code == OP_COMB) {
+            const Node& rn = *e.nodes[cur.ring_nodes[P.ops[i].aux & 0xff]];
+            if ((rn.D & 15) == 0 && rn.D >= 2 * (int64_t)S) {
+                P.pf_ring[P.n_prefetch] = (int16_t)(P.ops[i].aux & 0xff);
+                P.ops[i].aux = (uint16_t)((P.ops[i].aux & 0xff) | ((P.n_prefetch + 1) << 8));
+                P.n_prefetch++;
+                break;
+            }
+        }
+    char hdr[160];
+    snprintf(hdr, sizeof hdr, "fused segment: G=%d channels x S=%d samples per CTA, %d ops, %d smem vregs, %d prefetch slots\n", G,
+             S, P.n_ops, P.n_vregs, P.n_prefetch);
+    cur.text = hdr;
+    for (size_t i = 0; i < txt.size(); i++) cur.text += "    " + txt[i] + "\n";
+    steps.push_back(cur);
+    cur = Step();
+    ops.clear();
+    txt.clear();
+    next_vreg = 0;
+}
+
+int Lowerer::lower() {
+    const int N = (int)e.nodes.size();
+    // step assignment: ops of a node are emitted in the fused step open when it is visited; a Fir
+    // node closes that step (its input average is stored there) and gets its own step.
+    node_step.assign(N, 0);
+    {
+        int s = 0;
+        for (int ni : e.order) {
+            node_step[ni] = s;
+            if (e.nodes[ni]->type == T_FIR) s += 2;  // fused step s, FIR step s+1, next fused s+2
+        }
+        // NOTE: empty fused steps are still numbered; only relative order matters here.
+        for (int ni : e.order)
+            for (size_t p = 0; p < e.in_links[ni].size(); p++)
+                for (int l : e.in_links[ni][p]) {
+                    auto key = std::make_pair(e.links[l].src, e.links[l].sport);
+                    use_step[key] = std::max(use_step.count(key) ? use_step[key] : -1, node_step[ni]);
+                }
+    }
+    int state_slot = 0;
+    // `steps.size()` is not the step number used above (empty steps are dropped), so track it separately.
+    int logical_step = 0;
+    auto def_step_of = [&](int) { return logical_step; };
+    (void)def_step_of;
+    for (int ni : e.order) {
+        Node& nd = *e.nodes[ni];
+        const NodeType& nt = kNodeTypes[nd.type];
+        const std::string tag = std::string(nt.cfg_name) + "#" + std::to_string(nd.id);
+        auto out_value = [&](int port) {
+            // like save_value but with the logical step numbering
+            Value v;
+            auto key = std::make_pair(ni, port);
+            const int us = use_step.count(key) ? use_step[key] : -1;
+            if (us < 0) { v.where = Value::NONE; return v; }
+            if (us != logical_step) {
+                v.where = Value::GLOBAL;
+                v.bind_kind = 2;
+                v.bind_idx = n_scratch++;
+                Op o = mk(OP_STOREG);
+                o.buf = (uint8_t)buf_slot(2, v.bind_idx);
+                emit(o, "G" + std::to_string(o.buf) + " = acc                    ; " + tag + " (used in a later step)");
+            } else {
+                v.where = Value::VREG;
+                v.id = next_vreg++;
+                Op o = mk(OP_SAVEV);
+                o.vreg = (uint8_t)v.id;
+                emit(o, "v" + std::to_string(v.id) + " = acc                    ; " + tag + ".out");
+            }
+            return v;
+        };
+        auto ctl_param = [&](Op& op, int which, int pidx) {
+            // derive helper <field>_input (lib.rs:122-161): connected control port overrides the scalar
+            const ParamDef& pd = nt.params[pidx];
+            op.p[which] = nd.f32[pidx];
+            if (pd.ctl_port >= 0 && !e.in_links[ni][pd.ctl_port].empty()) {
+                emit_avg(ni, pd.ctl_port);
+                Op m = mk(OP_MODMAP);
+                m.p[0] = pd.lo;
+                m.p[1] = pd.hi;
+                emit(m, std::string("acc = map(acc, ") + std::to_string(pd.lo) + ", " + std::to_string(pd.hi) + ") ; " + tag + "." + pd.name + " control port");
+                int v = temp_save(tag + "." + pd.name);
+                op.pflags |= (1 << which);
+                op.pv[which] = (uint8_t)v;
+            }
+        };
+        auto alloc_state = [&](Op& op) -> int {
+            if (state_slot >= kMaxStates) { err = "too many stateful nodes in one graph step"; return -1; }
+            op.aux = (uint16_t)state_slot;
+            cur.prog.states[state_slot] = nd.state.p;
+            return state_slot++;
+        };
+        switch (nd.type) {
+            case T_INPUT: {
+                int t = (int)(std::find(e.in_terms.begin(), e.in_terms.end(), ni) - e.in_terms.begin());
+                Value v;
+                v.where = Value::GLOBAL;
+                v.bind_kind = 0;
+                v.bind_idx = t;
+                values[{ni, 0}] = v;
+            } break;
+            case T_OUTPUT: {
+                int t = (int)(std::find(e.out_terms.begin(), e.out_terms.end(), ni) - e.out_terms.begin());
+                emit_avg(ni, 0);  // nodes/output.rs:223
+                Op o = mk(OP_STOREG);
+                o.buf = (uint8_t)buf_slot(1, t);
+                emit(o, "G" + std::to_string(o.buf) + " = acc                    ; output terminal " + std::to_string(t));
+            } break;
+            case T_FIR: {
+                emit_avg(ni, 0);
+                Op o = mk(OP_STOREG);
+                o.buf = (uint8_t)buf_slot(3, ni);
+                emit(o, "G" + std::to_string(o.buf) + " = acc                    ; " + tag + " input (+history)");
+                close_fused();
+                Step fs;
+                fs.kind = STEP_FIR;
+                fs.fir_node = ni;
+                char b[160];
+                if (e.cfg.fir_mode == FIR_FFT)
+                    snprintf(b, sizeof b, "fir step: %s, %zu taps, overlap-save FFT 2^%d, two channels per transform\n", tag.c_str(),
+                             nd.taps.size(), e.cfg.fir_fft_log2);
+                else
+                    snprintf(b, sizeof b, "fir step: %s, %zu taps, direct f64 sum in reference order\n", tag.c_str(), nd.taps.size());
+                fs.text = b;
+                steps.push_back(fs);
+                logical_step += 2;
+                state_slot = 0;
+                memset(cur.prog.states, 0, sizeof cur.prog.states);
+                Value v;
+                v.where = Value::GLOBAL;
+                v.bind_kind = 4;
+                v.bind_idx = ni;
+                values[{ni, 0}] = v;
+            } break;
+            case T_MUX: {  // nodes/mux.rs:45-55: copy the selected (averaged) input
+                emit_avg(ni, nd.enums[0]);
+                values[{ni, 0}] = out_value(0);
+            } break;
+            case T_DEMUX: {  // nodes/demux.rs:45-58: the other output keeps its zero-init (node.rs:272)
+                const int sel = nd.enums[0];
+                Value z;
+                z.where = Value::ZERO;
+                values[{ni, 1 - sel}] = z;
+                if (use_step.count({ni, sel})) {
+                    emit_avg(ni, 0);
+                    values[{ni, sel}] = out_value(sel);
+                } else {
+                    values[{ni, sel}] = z;
+                }
+            } break;
+            case T_ADD:
+            case T_MIX: {
+                emit_avg(ni, 1);
+                int vb = temp_save(tag + ".b");
+                Op op = mk(nd.type == T_ADD ? OP_ADD : OP_MIX);
+                if (nd.type == T_MIX) ctl_param(op, 0, 0);
+                emit_avg(ni, 0);
+                op.vreg = (uint8_t)vb;
+                emit(op, nd.type == T_ADD ? "acc = acc + v" + std::to_string(vb) + "            ; " + tag
+                                          : "acc = v" + std::to_string(vb) + "*r + acc*(1-r)      ; " + tag);
+                values[{ni, 0}] = out_value(0);
+            } break;
+            case T_SIGGEN: {
+                err = "signal_gen is not lowered yet";
+                return DSPB_ERR_INVALID;
+            }
+            default: {  // single-input effect nodes
+                Op op = mk(OP_END);
+                std::string desc;
+                char b[160];
+                switch (nd.type) {
+                    case T_GAIN:
+                        op.code = OP_GAIN;
+                        ctl_param(op, 0, 0);
+                        snprintf(b, sizeof b, "acc *= level(%g)", nd.f32[0]);
+                        break;
+                    case T_DISTORT:
+                        op.code = OP_DISTORT;
+                        op.mode = (uint8_t)nd.enums[0];
+                        ctl_param(op, 0, 0);
+                        snprintf(b, sizeof b, "acc = distort[%s](acc, %g)", nt.enums[0].variants[nd.enums[0]], nd.f32[0]);
+                        break;
+                    case T_OVERDRIVE:
+                        op.code = OP_OVERDRIVE;
+                        ctl_param(op, 0, 0);
+                        ctl_param(op, 1, 1);
+                        ctl_param(op, 2, 2);
+                        snprintf(b, sizeof b, "acc = overdrive(acc, %g, %g, %g)", nd.f32[0], nd.f32[1], nd.f32[2]);
+                        break;
+                    case T_CHEBY:
+                        op.code = OP_CHEBY;
+                        op.p[0] = nd.f32[0];
+                        op.p[1] = nd.f32[1];
+                        op.p[2] = std::tanh(nd.f32[0]);  // level.tanh(): libm tanhf, as the reference host would
+                        op.p[3] = std::tanh(nd.f32[1]);
+                        snprintf(b, sizeof b, "acc = chebyshev(acc, %g, %g)", nd.f32[0], nd.f32[1]);
+                        break;
+                    case T_BIQUAD:
+                        op.code = OP_BIQUAD;
+                        for (int i = 0; i < 5; i++) op.p[i] = nd.bq[i];
+                        snprintf(b, sizeof b, "acc = DF1(acc; b=%g,%g,%g a=%g,%g) exact, lane=channel", nd.bq[0], nd.bq[1], nd.bq[2], nd.bq[3], nd.bq[4]);
+                        break;
+                    case T_LOWPASS:
+                    case T_HIGHPASS:
+                        op.code = nd.type == T_LOWPASS ? OP_LP1 : OP_HP1;
+                        op.p[0] = nd.f32[0];
+                        op.p[1] = 1.0f - nd.f32[0];
+                        snprintf(b, sizeof b, "acc = %s(acc; ratio=%g) exact, lane=channel", nt.cfg_name, nd.f32[0]);
+                        break;
+                    case T_ENVELOPE:
+                        op.code = OP_ENVELOPE;
+                        op.p[0] = nd.f32[0] == 0.0f ? 0.0f : std::exp(-1.0f / nd.f32[0]);  // dasp calc_gain
+                        op.p[1] = nd.f32[1] == 0.0f ? 0.0f : std::exp(-1.0f / nd.f32[1]);
+                        snprintf(b, sizeof b, "acc = envelope(acc; ga=%g gr=%g) exact, lane=channel", op.p[0], op.p[1]);
+                        break;
+                    case T_REVERB:
+                        op.code = OP_COMB;
+                        op.p[0] = nd.f32[1];
+                        if ((int)cur.ring_nodes.size() >= kMaxRings) { err = "too many reverb nodes in one step"; return DSPB_ERR_INVALID; }
+                        op.aux = (uint16_t)cur.ring_nodes.size();
+                        cur.ring_nodes.push_back(ni);
+                        snprintf(b, sizeof b, "acc += ring*%g ; ring = acc   (D=%lld)", nd.f32[1], (long long)nd.D);
+                        break;
+                    default:
+                        err = "unhandled node type";
+                        return DSPB_ERR_INVALID;
+                }
+                emit_avg(ni, 0);
+                if (is_stateful(nd.type) && alloc_state(op) < 0) return DSPB_ERR_INVALID;
+                emit(op, std::string(b) + "  ; " + tag);
+                values[{ni, 0}] = out_value(0);
+            } break;
+        }
+        if (!err.empty()) return DSPB_ERR_INVALID;
+    }
+    close_fused();
+    return err.empty() ? DSPB_OK : DSPB_ERR_INVALID;
+}
+
+int ensure_resources(dspb_engine* e) {
+    const int C = e->cfg.channels;
+    const int64_t maxn = e->cfg.max_samples;
+    for (auto& np : e->nodes) {
+        Node& n = *np;
+        if (is_stateful(n.type) && !n.state.p) {
+            int r = n.state.alloc((size_t)C * 16, true);
+            if (r) return r;
+        }
+        if (n.type == T_REVERB && (n.ring_dirty || !n.ring.p)) {
+            int r = n.ring.alloc((size_t)C * n.D * 4, true);  // "full of zeros": reverb.rs:63-68
+            if (r) return r;
+            n.pos = 0;
+            n.ring_dirty = false;
+        }
+        if (n.type == T_FIR && (n.fir_dirty || !n.Y.p)) {
+            const int N = (int)n.taps.size();
+            const int F = 1 << e->cfg.fir_fft_log2;
+            if (N > F / 2) return fail(DSPB_ERR_INVALID, "fir: %d taps need fir_fft_log2 > %d", N, e->cfg.fir_fft_log2);
+            n.hist_pad = (int)round_up(std::max(N - 1, 4), 4);
+            for (auto& u : n.U) {
+                int r = u.alloc((size_t)C * (n.hist_pad + maxn) * 4, true);
+                if (r) return r;
+            }
+            int r = n.Y.alloc((size_t)C * maxn * 4, false);
+            if (r) return r;
+            r = n.H.alloc((size_t)F * 8, false);
+            if (r) return r;
+            r = n.taps_dev.alloc((size_t)N * 8, false);
+            if (r) return r;
+            if (!e->plan_only) {
+                CUDA_TRY(cudaMemcpy(n.taps_dev.p, n.taps.data(), (size_t)N * 8, cudaMemcpyHostToDevice));
+                int rc = fir_prepare_spectrum(e->cfg.fir_fft_log2, n.taps.data(), N, reinterpret_cast<float2*>(n.H.p), nullptr);
+                if (rc) return fail(DSPB_ERR_CUDA, "fir_prepare_spectrum: %s", cudaGetErrorString((cudaError_t)rc));
+                CUDA_TRY(cudaDeviceSynchronize());
+            }
+            n.started = 0;
+            n.cur_u = 0;
+            n.fir_dirty = false;
+        }
+    }
+    return DSPB_OK;
+}
+
+int lower_graph(dspb_engine* e) {
+    int r = ensure_resources(e);
+    if (r) return r;
+    Lowerer L(*e);
+    r = L.lower();
+    if (r) return fail(r, "lowering failed: %s", L.err.c_str());
+    e->steps = std::move(L.steps);
+    while ((int)e->scratch.size() < L.n_scratch) {
+        auto b = std::make_unique<DevBuf>();
+        r = b->alloc((size_t)e->cfg.channels * e->cfg.max_samples * 4, false);
+        if (r) return r;
+        e->scratch.push_back(std::move(b));
+    }
+    for (auto& st : e->steps)
+        if (st.kind == STEP_FUSED && fused_smem_bytes(st.prog, st.G) > 200 * 1024)
+            return fail(DSPB_ERR_INVALID, "fused segment needs %d B of shared memory (too many live values)", fused_smem_bytes(st.prog, st.G));
+    e->lowered = true;
+    return DSPB_OK;
+}
+
+int topo_sort(dspb_engine* e) {
+    const int N = (int)e->nodes.size();
+    e->in_links.assign(N, {});
+    e->out_links.assign(N, {});
+    for (int i = 0; i < N; i++) {
+        e->in_links[i].assign(kNodeTypes[e->nodes[i]->type].ins.size(), {});
+        e->out_links[i].assign(kNodeTypes[e->nodes[i]->type].outs.size(), {});
+    }
+    std::vector<int> indeg(N, 0), nlinks(N, 0);
+    for (size_t l = 0; l < e->links.size(); l++) {
+        const Link& k = e->links[l];
+        e->in_links[k.dst][k.dport].push_back((int)l);  // link-creation order (runtime.rs:125-134)
+        e->out_links[k.src][k.sport].push_back((int)l);
+        indeg[k.dst]++;
+        nlinks[k.src]++;
+        nlinks[k.dst]++;
+    }
+    e->in_terms.clear();
+    e->out_terms.clear();
+    for (int i = 0; i < N; i++) {
+        if (e->nodes[i]->type == T_INPUT) e->in_terms.push_back(i);
+        if (e->nodes[i]->type == T_OUTPUT) e->out_terms.push_back(i);
+    }
+    // Depth-first Kahn (LIFO ready list) keeps chains contiguous so values stay in registers;
+    // nodes with no links at all never run (runtime.rs:661-668).
+    e->order.clear();
+    std::vector<int> ready;
+    for (int i = N - 1; i >= 0; i--)
+        if (indeg[i] == 0) ready.push_back(i);
+    int seen = 0;
+    while (!ready.empty()) {
+        int n = ready.back();
+        ready.pop_back();
+        seen++;
+        if (nlinks[n] > 0) e->order.push_back(n);
+        for (int q = (int)e->out_links[n].size() - 1; q >= 0; q--)
+            for (int li = (int)e->out_links[n][q].size() - 1; li >= 0; li--) {
+                int d = e->links[e->out_links[n][q][li]].dst;
+                if (--indeg[d] == 0) ready.push_back(d);
+            }
+    }
+    if (seen != N) return fail(DSPB_ERR_GRAPH, "graph has a cycle (the reference would deadlock: every link ring starts empty, runtime.rs:568)");
+    return DSPB_OK;
+}
+
+// Bind per-call pointers and launch every step for channels [c0, c1).
+int run_steps(dspb_engine* e, const float* const* d_in, float* const* d_out, int64_t n, int c0, int c1, cudaStream_t st) {
+    for (auto& s : e->steps) {
+        if (s.kind == STEP_FUSED) {
+            Program& P = s.prog;
+            for (size_t b = 0; b < s.binds.size(); b++) {
+                BufDesc& d = P.bufs[b];
+                switch (s.binds[b].kind) {
+                    case 0: d.base = const_cast<float*>(d_in[s.binds[b].idx]); d.row_stride = n; break;
+                    case 1: d.base = d_out[s.binds[b].idx]; d.row_stride = n; break;
+                    case 2: d.base = e->scratch[s.binds[b].idx]->p; d.row_stride = e->cfg.max_samples; break;
+                    case 3: {
+                        Node& f = *e->nodes[s.binds[b].idx];
+                        d.row_stride = f.hist_pad + e->cfg.max_samples;
+                        d.base = f.U[f.cur_u].p + f.hist_pad;
+                    } break;
+                    case 4: {
+                        Node& f = *e->nodes[s.binds[b].idx];
+                        d.base = f.Y.p;
+                        d.row_stride = e->cfg.max_samples;
+                    } break;
+                }
+            }
+            for (size_t r = 0; r < s.ring_nodes.size(); r++) {
+                Node& rn = *e->nodes[s.ring_nodes[r]];
+                P.rings[r].base = rn.ring.p;
+                P.rings[r].D = rn.D;
+                P.rings[r].pos = rn.pos;
+            }
+            int rc = launch_fused(P, s.G, c0, c1, n, st);
+            if (rc) return fail(DSPB_ERR_CUDA, "fused kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+            e->last_launches++;
+        } else {
+            Node& f = *e->nodes[s.fir_node];
+            FirPlan fp;
+            fp.mode = e->cfg.fir_mode;
+            fp.log2F = e->cfg.fir_fft_log2;
+            fp.n_taps = (int)f.taps.size();
+            fp.hist_pad = f.hist_pad;
+            fp.H = reinterpret_cast<const float2*>(f.H.p);
+            fp.taps = reinterpret_cast<const double*>(f.taps_dev.p);
+            fp.divisor = f.enums[0] == 0 ? 1.0f / (float)f.taps.size() : 1.0f;  // fir.rs:187-190
+            const int64_t us = f.hist_pad + e->cfg.max_samples;
+            int nl = 0;
+            int rc = launch_fir(fp, f.U[f.cur_u].p, us, f.Y.p, e->cfg.max_samples, c0, c1, n, f.started, st, &nl);
+            if (rc) return fail(DSPB_ERR_CUDA, "fir kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+            e->last_launches += nl;
+            // carry the last hist_pad samples into the other U buffer (front) for the next call
+            for (int c = c0; c < c1; c += 4096) {
+                const int cc = std::min(c1, c + 4096) - c;
+                CUDA_TRY(cudaMemcpy2DAsync(f.U[f.cur_u ^ 1].p + (size_t)c * us, us * 4, f.U[f.cur_u].p + (size_t)c * us + n, us * 4,
+                                           (size_t)f.hist_pad * 4, cc, cudaMemcpyDeviceToDevice, st));
+            }
+        }
+    }
+    return DSPB_OK;
+}
+
+void advance_state(dspb_engine* e, int64_t n) {
+    for (auto& np : e->nodes) {
+        Node& nd = *np;
+        if (nd.type == T_REVERB && nd.D > 0) nd.pos = (nd.pos + n) % nd.D;
+        if (nd.type == T_FIR) { nd.started += n; nd.cur_u ^= 1; }
+    }
+}
+
+int check_ready(dspb_engine* e, int64_t n) {
+    if (!e->compiled) return fail(DSPB_ERR_GRAPH, "graph not compiled (call dspb_compile after structural changes)");
+    if (n <= 0 || n % e->cfg.ref_block) return fail(DSPB_ERR_INVALID, "n_samples must be a positive multiple of %d", e->cfg.ref_block);
+    if (n > e->cfg.max_samples) return fail(DSPB_ERR_INVALID, "n_samples %lld exceeds max_samples %lld", (long long)n, (long long)e->cfg.max_samples);
+    if (!e->lowered) {
+        int r = lower_graph(e);
+        if (r) return r;
+    }
+    return DSPB_OK;
+}
+
+}  // namespace
+
+// =================================================== C ABI =====================================================
+extern "C" {
+
+const char* dspb_last_error(void) { return g_err.c_str(); }
+int dspb_abi_version(void) { return DSPB_ABI_VERSION; }
+
+int dspb_engine_create(const dspb_config* cfg, dspb_engine** out) {
+    if (!cfg || !out) return fail(DSPB_ERR_INVALID, "null argument");
+    if (cfg->channels <= 0) return fail(DSPB_ERR_INVALID, "channels must be > 0");
+    const bool plan_only = cfg->device == -1;  // schedules can be built and described, nothing can run
+    if (!plan_only) {
+        int ndev = 0;
+        cudaError_t ce = cudaGetDeviceCount(&ndev);
+        if (ce != cudaSuccess || ndev == 0)
+            return fail(DSPB_ERR_CUDA, "no usable CUDA device (%s); this engine has no CPU fallback", ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+        if (cfg->device < 0 || cfg->device >= ndev) return fail(DSPB_ERR_INVALID, "device %d out of range (have %d)", cfg->device, ndev);
+        CUDA_TRY(cudaSetDevice(cfg->device));
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+        if (prop.major < 10) return fail(DSPB_ERR_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
+    }
+    g_plan_only = plan_only;
+    auto* e = new dspb_engine();
+    e->plan_only = plan_only;
+    e->cfg = *cfg;
+    if (e->cfg.sample_rate <= 0) e->cfg.sample_rate = 48000;
+    if (e->cfg.ref_block <= 0) e->cfg.ref_block = kRefBlock;
+    if (e->cfg.ref_block != kRefBlock) { delete e; return fail(DSPB_ERR_INVALID, "ref_block must be 128 (node.rs:257)"); }
+    if (e->cfg.block <= 0) e->cfg.block = kRefBlock;
+    if (e->cfg.block % kRefBlock) { delete e; return fail(DSPB_ERR_INVALID, "block must be a multiple of 128"); }
+    if (e->cfg.ring_granule <= 0) e->cfg.ring_granule = 1024;
+    if (e->cfg.max_samples <= 0) e->cfg.max_samples = 64 * (int64_t)e->cfg.block;
+    e->cfg.max_samples = round_up(e->cfg.max_samples, kRefBlock);
+    if (e->cfg.fir_fft_log2 <= 0) e->cfg.fir_fft_log2 = 13;
+    if (e->cfg.fir_fft_log2 != 13) { delete e; return fail(DSPB_ERR_INVALID, "fir_fft_log2 must be 13 in this build"); }
+    if (e->cfg.fir_mode != FIR_FFT && e->cfg.fir_mode != FIR_DIRECT) { delete e; return fail(DSPB_ERR_INVALID, "fir_mode must be 0 (FFT) or 1 (direct)"); }
+    if (const char* g = getenv("DSPB_FORCE_G")) e->force_G = atoi(g);
+    *out = e;
+    return DSPB_OK;
+}
+
+void dspb_engine_destroy(dspb_engine* e) {
+    if (!e) return;
+    if (!e->plan_only) {
+        cudaSetDevice(e->cfg.device);
+        cudaDeviceSynchronize();
+    }
+    delete e;
+}
+
+int dspb_node_add(dspb_engine* e, const char* cfg_name, int64_t node_id) {
+    if (!e || !cfg_name) return fail(DSPB_ERR_INVALID, "null argument");
+    if (e->find(node_id) >= 0) return fail(DSPB_ERR_INVALID, "duplicate node id %lld", (long long)node_id);
+    int type = -1;
+    for (int t = 0; t < T_COUNT; t++)
+        if (!strcmp(kNodeTypes[t].cfg_name, cfg_name)) type = t;
+    if (type < 0) return fail(DSPB_ERR_UNKNOWN_NODE, "unknown typename '%s' (reference: panic in NodeInstance::restore, runtime.rs:634-637)", cfg_name);
+    auto n = std::make_unique<Node>();
+    n->id = node_id;
+    n->type = type;
+    for (auto& p : kNodeTypes[type].params) n->f32.push_back(p.def);
+    for (auto& en : kNodeTypes[type].enums) n->enums.push_back(en.def);
+    if (type == T_REVERB) n->D = round_up(128, e->cfg.ring_granule);  // make_buffer(): circular_buffer(128), reverb.rs:44-52
+    e->nodes.push_back(std::move(n));
+    e->compiled = e->lowered = false;
+    return DSPB_OK;
+}
+
+int dspb_node_set_f32(dspb_engine* e, int64_t node_id, const char* field, float value) {
+    if (!e || !field) return fail(DSPB_ERR_INVALID, "null argument");
+    int i = e->find(node_id);
+    if (i < 0) return fail(DSPB_ERR_UNKNOWN_NODE, "unknown node id %lld", (long long)node_id);
+    Node& n = *e->nodes[i];
+    int p = param_index(kNodeTypes[n.type], field);
+    if (p < 0) return fail(DSPB_ERR_UNKNOWN_PORT, "node type '%s' has no f32 field '%s'", kNodeTypes[n.type].cfg_name, field);
+    n.f32[p] = value;
+    if (!e->plan_only) CUDA_TRY(cudaSetDevice(e->cfg.device));
+    if (n.type == T_BIQUAD) {  // after_settings_change = regenerate_filter: new coefficients + reset_state
+        biquad_regenerate(n);
+        if (n.state.p && !e->plan_only) CUDA_TRY(cudaMemsetAsync(n.state.p, 0, n.state.bytes, nullptr));
+    }
+    if (n.type == T_REVERB) {  // after_settings_change = refresh_seconds on ANY slider of the node (lib.rs:560-568)
+        n.D = reverb_delay(n.f32[0], e->cfg.sample_rate, e->cfg.ring_granule);
+        n.ring_dirty = true;
+    }
+    e->lowered = false;
+    return DSPB_OK;
+}
+
+int dspb_node_set_enum(dspb_engine* e, int64_t node_id, const char* field, const char* variant) {
+    if (!e || !field || !variant) return fail(DSPB_ERR_INVALID, "null argument");
+    int i = e->find(node_id);
+    if (i < 0) return fail(DSPB_ERR_UNKNOWN_NODE, "unknown node id %lld", (long long)node_id);
+    Node& n = *e->nodes[i];
+    const NodeType& nt = kNodeTypes[n.type];
+    for (size_t k = 0; k < nt.enums.size(); k++)
+        if (!strcmp(nt.enums[k].name, field)) {
+            for (size_t v = 0; v < nt.enums[k].variants.size(); v++)
+                if (!strcmp(nt.enums[k].variants[v], variant)) {
+                    n.enums[k] = (int)v;
+                    e->lowered = false;
+                    return DSPB_OK;
+                }
+            return fail(DSPB_ERR_UNKNOWN_PORT, "enum field '%s' has no variant '%s'", field, variant);
+        }
+    return fail(DSPB_ERR_UNKNOWN_PORT, "node type '%s' has no enum field '%s'", nt.cfg_name, field);
+}
+
+int dspb_node_set_taps(dspb_engine* e, int64_t node_id, const double* taps, int64_t n_taps) {
+    if (!e || !taps || n_taps <= 0) return fail(DSPB_ERR_INVALID, "bad taps");
+    int i = e->find(node_id);
+    if (i < 0) return fail(DSPB_ERR_UNKNOWN_NODE, "unknown node id %lld", (long long)node_id);
+    Node& n = *e->nodes[i];
+    if (n.type != T_FIR) return fail(DSPB_ERR_INVALID, "node %lld is not a fir", (long long)node_id);
+    n.taps.assign(taps, taps + n_taps);
+    n.fir_dirty = true;
+    e->lowered = false;
+    return DSPB_OK;
+}
+
+int dspb_node_set_impulse_response(dspb_engine* e, int64_t node_id, const double* h, int64_t n) {
+    if (!h || n <= 0) return fail(DSPB_ERR_INVALID, "bad impulse response");
+    std::vector<double> rev(h, h + n);
+    std::reverse(rev.begin(), rev.end());  // taps.reverse(), nodes/fir.rs:163-168
+    return dspb_node_set_taps(e, node_id, rev.data(), n);
+}
+
+int dspb_link(dspb_engine* e, int64_t src_node, const char* out_port, int64_t dst_node, const char* in_port) {
+    if (!e || !out_port || !in_port) return fail(DSPB_ERR_INVALID, "null argument");
+    int s = e->find(src_node), d = e->find(dst_node);
+    if (s < 0 || d < 0) return fail(DSPB_ERR_UNKNOWN_NODE, "unknown node id in link %lld -> %lld", (long long)src_node, (long long)dst_node);
+    int sp = port_index(kNodeTypes[e->nodes[s]->type].outs, out_port);
+    int dp = port_index(kNodeTypes[e->nodes[d]->type].ins, in_port);
+    if (sp < 0) return fail(DSPB_ERR_UNKNOWN_PORT, "node type '%s' has no output port '%s'", kNodeTypes[e->nodes[s]->type].cfg_name, out_port);
+    if (dp < 0) return fail(DSPB_ERR_UNKNOWN_PORT, "node type '%s' has no input port '%s'", kNodeTypes[e->nodes[d]->type].cfg_name, in_port);
+    e->links.push_back(Link{s, sp, d, dp});
+    e->compiled = e->lowered = false;
+    return DSPB_OK;
+}
+
+int dspb_compile(dspb_engine* e) {
+    if (!e) return fail(DSPB_ERR_INVALID, "null engine");
+    g_plan_only = e->plan_only;
+    if (!e->plan_only) CUDA_TRY(cudaSetDevice(e->cfg.device));
+    int r = topo_sort(e);
+    if (r) return r;
+    e->compiled = true;
+    e->lowered = false;
+    return lower_graph(e);
+}
+
+int dspb_reset_state(dspb_engine* e) {
+    if (!e) return fail(DSPB_ERR_INVALID, "null engine");
+    if (e->plan_only) return fail(DSPB_ERR_CUDA, "planning-only engine (device -1) holds no state");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (auto& n : e->nodes) {
+        int r = clear_node_state(e, *n);
+        if (r) return r;
+    }
+    return DSPB_OK;
+}
+
+int dspb_process(dspb_engine* e, const float* const* inputs, float* const* outputs, int64_t n, int mem_kind, void* stream) {
+    if (!e) return fail(DSPB_ERR_INVALID, "null engine");
+    if (e->plan_only) return fail(DSPB_ERR_CUDA, "planning-only engine (device -1) cannot process: there is no CPU fallback");
+    g_plan_only = false;
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    int r = check_ready(e, n);
+    if (r) return r;
+    const int C = e->cfg.channels;
+    const size_t n_in = e->in_terms.size(), n_out = e->out_terms.size();
+    if ((n_in && !inputs) || (n_out && !outputs)) return fail(DSPB_ERR_INVALID, "null buffer table");
+    for (size_t i = 0; i < n_in; i++)
+        if (!inputs[i]) return fail(DSPB_ERR_INVALID, "null input buffer %zu", i);
+    for (size_t i = 0; i < n_out; i++)
+        if (!outputs[i]) return fail(DSPB_ERR_INVALID, "null output buffer %zu", i);
+    e->last_launches = 0;
+    if (mem_kind == DSPB_MEM_DEVICE) {
+        for (size_t i = 0; i < n_in; i++)
+            if ((uintptr_t)inputs[i] & 15) return fail(DSPB_ERR_INVALID, "device buffers must be 16-byte aligned");
+        for (size_t i = 0; i < n_out; i++)
+            if ((uintptr_t)outputs[i] & 15) return fail(DSPB_ERR_INVALID, "device buffers must be 16-byte aligned");
+        r = run_steps(e, inputs, outputs, n, 0, C, (cudaStream_t)stream);
+        if (r) return r;
+        advance_state(e, n);
+        return DSPB_OK;
+    }
+    if (mem_kind != DSPB_MEM_HOST) return fail(DSPB_ERR_INVALID, "mem_kind must be DSPB_MEM_DEVICE or DSPB_MEM_HOST");
+    // Host buffers: channel ranges are independent, so H2D / kernels / D2H of successive channel
+    // chunks overlap on three streams.
+    if (!e->s_cmp) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&e->s_cmp, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&e->s_d2h, cudaStreamNonBlocking));
+    }
+    while (e->h_in.size() < n_in) {
+        auto b = std::make_unique<DevBuf>();
+        r = b->alloc((size_t)C * e->cfg.max_samples * 4, false);
+        if (r) return r;
+        e->h_in.push_back(std::move(b));
+    }
+    while (e->h_out.size() < n_out) {
+        auto b = std::make_unique<DevBuf>();
+        r = b->alloc((size_t)C * e->cfg.max_samples * 4, false);
+        if (r) return r;
+        e->h_out.push_back(std::move(b));
+    }
+    std::vector<const float*> din(n_in);
+    std::vector<float*> dout(n_out);
+    for (size_t i = 0; i < n_in; i++) din[i] = e->h_in[i]->p;
+    for (size_t i = 0; i < n_out; i++) dout[i] = e->h_out[i]->p;
+    int n_chunks = 8;
+    int per = (C + n_chunks - 1) / n_chunks;
+    per = (per + 31) / 32 * 32;  // keep CTA channel groups intact
+    n_chunks = (C + per - 1) / per;
+    while ((int)e->ev_pool.size() < 2 * n_chunks) {
+        cudaEvent_t ev;
+        CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        e->ev_pool.push_back(ev);
+    }
+    for (int k = 0; k < n_chunks; k++) {
+        const int c0 = k * per, c1 = std::min(C, c0 + per);
+        for (size_t i = 0; i < n_in; i++)
+            CUDA_TRY(cudaMemcpyAsync(e->h_in[i]->p + (size_t)c0 * n, inputs[i] + (size_t)c0 * n, (size_t)(c1 - c0) * n * 4, cudaMemcpyHostToDevice, e->s_h2d));
+        CUDA_TRY(cudaEventRecord(e->ev_pool[2 * k], e->s_h2d));
+        CUDA_TRY(cudaStreamWaitEvent(e->s_cmp, e->ev_pool[2 * k], 0));
+        r = run_steps(e, din.data(), dout.data(), n, c0, c1, e->s_cmp);
+        if (r) return r;
+        CUDA_TRY(cudaEventRecord(e->ev_pool[2 * k + 1], e->s_cmp));
+        CUDA_TRY(cudaStreamWaitEvent(e->s_d2h, e->ev_pool[2 * k + 1], 0));
+        for (size_t i = 0; i < n_out; i++)
+            CUDA_TRY(cudaMemcpyAsync(outputs[i] + (size_t)c0 * n, e->h_out[i]->p + (size_t)c0 * n, (size_t)(c1 - c0) * n * 4, cudaMemcpyDeviceToHost, e->s_d2h));
+    }
+    CUDA_TRY(cudaStreamSynchronize(e->s_d2h));
+    CUDA_TRY(cudaStreamSynchronize(e->s_cmp));
+    advance_state(e, n);
+    return DSPB_OK;
+}
+
+int dspb_node_get_i64(dspb_engine* e, int64_t node_id, const char* key, int64_t* out) {
+    if (!e || !key || !out) return fail(DSPB_ERR_INVALID, "null argument");
+    if (!strcmp(key, "kernel_launches")) { *out = e->last_launches; return DSPB_OK; }
+    if (!strcmp(key, "n_segments")) { *out = (int64_t)e->steps.size(); return DSPB_OK; }
+    int i = e->find(node_id);
+    if (i < 0) return fail(DSPB_ERR_UNKNOWN_NODE, "unknown node id %lld", (long long)node_id);
+    Node& n = *e->nodes[i];
+    if (!strcmp(key, "n_inputs")) { *out = (int64_t)kNodeTypes[n.type].ins.size(); return DSPB_OK; }
+    if (!strcmp(key, "n_outputs")) { *out = (int64_t)kNodeTypes[n.type].outs.size(); return DSPB_OK; }
+    if (!strcmp(key, "delay_samples") && n.type == T_REVERB) { *out = n.D; return DSPB_OK; }
+    if (!strcmp(key, "ring_pos") && n.type == T_REVERB) { *out = n.pos; return DSPB_OK; }
+    if (!strcmp(key, "n_taps") && n.type == T_FIR) { *out = (int64_t)n.taps.size(); return DSPB_OK; }
+    return fail(DSPB_ERR_UNKNOWN_PORT, "node type '%s' has no key '%s'", kNodeTypes[n.type].cfg_name, key);
+}
+
+int dspb_node_port_index(dspb_engine* e, int64_t node_id, const char* port, int is_output, int32_t* out) {
+    if (!e || !port || !out) return fail(DSPB_ERR_INVALID, "null argument");
+    int i = e->find(node_id);
+    if (i < 0) return fail(DSPB_ERR_UNKNOWN_NODE, "unknown node id %lld", (long long)node_id);
+    const NodeType& nt = kNodeTypes[e->nodes[i]->type];
+    int p = port_index(is_output ? nt.outs : nt.ins, port);
+    if (p < 0) return fail(DSPB_ERR_UNKNOWN_PORT, "node type '%s' has no %s port '%s'", nt.cfg_name, is_output ? "output" : "input", port);
+    *out = p;
+    return DSPB_OK;
+}
+
+int64_t dspb_describe_plan(dspb_engine* e, char* buf, int64_t cap) {
+    if (!e) return 0;
+    std::string s;
+    char b[128];
+    snprintf(b, sizeof b, "plan: %d channels, %zu step(s)\n", e->cfg.channels, e->steps.size());
+    s += b;
+    int k = 0;
+    for (auto& st : e->steps) {
+        snprintf(b, sizeof b, "[%d] ", k++);
+        s += b;
+        s += st.text;
+    }
+    if (buf && cap > 0) {
+        size_t n = std::min<size_t>(s.size(), (size_t)cap - 1);
+        memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int64_t)s.size() + 1;
+}
+
+// ---- single-node call: SimpleNode::process on pre-averaged port buffers ----------------------------------------
+int dspb_node_process(dspb_engine* e, int64_t node_id, const float* const* port_inputs, const uint8_t* present,
+                      float* const* port_outputs, int64_t n, int mem_kind, void* stream) {
+    (void)e; (void)node_id; (void)port_inputs; (void)present; (void)port_outputs; (void)n; (void)mem_kind; (void)stream;
+    return fail(DSPB_ERR_INVALID, "dspb_node_process: not implemented in this build");
+}
+
+// ---- saved-graph JSON (runtime.rs:44-48, 94-123, 560-564, 606-612; lib.rs:266-340) ------------------------------
+int dspb_load_graph_json(dspb_engine* e, const char* text) {
+    if (!e || !text) return fail(DSPB_ERR_INVALID, "null argument");
+    if (!e->nodes.empty()) return fail(DSPB_ERR_GRAPH, "dspb_load_graph_json needs an empty engine");
+    jsonmin::Value doc;
+    std::string perr;
+    if (!jsonmin::parse(text, doc, perr)) return fail(DSPB_ERR_PARSE, "graph JSON: %s", perr.c_str());
+    const jsonmin::Value* nodes = doc.get("nodes");
+    const jsonmin::Value* links = doc.get("links");
+    if (!nodes || !nodes->is_array() || !links || !links->is_array()) return fail(DSPB_ERR_PARSE, "graph JSON: need 'nodes' and 'links' arrays");
+    std::map<std::pair<int64_t, int64_t>, std::pair<std::string, bool>> port_names;  // (node, PortId) -> (name, is_output)
+    for (const auto& nv : nodes->arr) {
+        const jsonmin::Value* id = nv.get("id");
+        const jsonmin::Value* tn = nv.get("typename");
+        const jsonmin::Value* cfg = nv.get("cfg");
+        if (!id || !id->is_number() || !tn || !tn->is_string() || !cfg || !cfg->is_object()) return fail(DSPB_ERR_PARSE, "graph JSON: malformed node entry");
+        const int64_t nid = (int64_t)id->num;
+        int r = dspb_node_add(e, tn->str.c_str(), nid);
+        if (r) return r;
+        Node& n = *e->nodes.back();
+        for (const auto& kv : cfg->obj) {
+            const std::string& k = kv.first;
+            const jsonmin::Value& v = kv.second;
+            if (k == "id" || k == "file_name") continue;
+            if (k == "inputs" || k == "outputs") {
+                if (!v.is_object()) return fail(DSPB_ERR_PARSE, "graph JSON: '%s' must be a name -> PortId map", k.c_str());
+                for (const auto& pv : v.obj) port_names[{nid, (int64_t)pv.second.num}] = {pv.first, k == "outputs"};
+                continue;
+            }
+            if (k == "taps") {
+                if (!v.is_array()) return fail(DSPB_ERR_PARSE, "graph JSON: taps must be an array");
+                std::vector<double> t;
+                for (const auto& x : v.arr) t.push_back(x.num);
+                r = dspb_node_set_taps(e, nid, t.data(), (int64_t)t.size());
+            } else if (v.is_string()) {
+                r = dspb_node_set_enum(e, nid, k.c_str(), v.str.c_str());
+            } else if (v.is_number()) {
+                r = dspb_node_set_f32(e, nid, k.c_str(), (float)v.num);
+            } else {
+                continue;
+            }
+            if (r) return r;
+        }
+        // restore() runs after_settings_change unconditionally (lib.rs:319-336)
+        if (n.type == T_REVERB) { n.D = reverb_delay(n.f32[0], e->cfg.sample_rate, e->cfg.ring_granule); n.ring_dirty = true; }
+        if (n.type == T_BIQUAD) biquad_regenerate(n);
+    }
+    for (const auto& lv : links->arr) {
+        const jsonmin::Value* lhs = lv.get("lhs");
+        const jsonmin::Value* rhs = lv.get("rhs");
+        if (!lhs || !rhs || !lhs->is_array() || !rhs->is_array() || lhs->arr.size() != 2 || rhs->arr.size() != 2)
+            return fail(DSPB_ERR_PARSE, "graph JSON: malformed link entry");
+        const int64_t sn = (int64_t)lhs->arr[0].num, sp = (int64_t)lhs->arr[1].num;
+        const int64_t dn = (int64_t)rhs->arr[0].num, dp = (int64_t)rhs->arr[1].num;
+        auto a = port_names.find({sn, sp});
+        auto b = port_names.find({dn, dp});
+        if (a == port_names.end() || b == port_names.end() || !a->second.second || b->second.second)
+            return fail(DSPB_ERR_UNKNOWN_PORT, "graph JSON: link refers to an unknown PortId");
+        int r = dspb_link(e, sn, a->second.first.c_str(), dn, b->second.first.c_str());
+        if (r) return r;
+    }
+    return dspb_compile(e);
+}
+
+}  // extern "C"

@@ -1,0 +1,114 @@
+// plan.h — the device-side "program" a fused segment executes, shared by the host scheduler
+// (engine.cpp) and the kernels (fused_chain.cu, fir_fft.cu).
+//
+// One fused kernel runs a straight-line program over a tile of [G channels x S samples]
+// (G*S = 4096, 256 threads, 16 consecutive samples of one channel per thread).  The program is an
+// accumulator machine: `acc` is the thread's 16 samples in registers; other live values sit in
+// thread-private shared-memory "vregs" or in global scratch.  Recurrences (biquad, one-pole,
+// envelope) run lane = channel, strictly sequential in time, so they are bit-identical to the
+// reference arithmetic (DESIGN.md "IIR exactness").
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace dspb {
+
+constexpr int kThreads = 256;       // threads per CTA
+constexpr int kChunk = 16;          // consecutive samples per thread
+constexpr int kTile = kThreads * kChunk;  // 4096 samples per CTA tile
+constexpr int kRefBlock = 128;      // node.rs:257 BUF_SIZE
+constexpr int kMaxOps = 56;
+constexpr int kMaxBufs = 12;
+constexpr int kMaxRings = 6;
+constexpr int kMaxStates = 12;
+constexpr int kMaxPrefetch = 2;
+
+enum OpCode : uint8_t {
+    OP_END = 0,
+    OP_ZERO,       // acc = 0
+    OP_LOADG,      // acc = 0.0f + G[buf]           (first link of a fan-in sum, node.rs:181-183)
+    OP_ADDG,       // acc = acc + G[buf]
+    OP_LOADV,      // acc = 0.0f + V[vreg]
+    OP_ADDV,       // acc = acc + V[vreg]
+    OP_COPYV,      // acc = V[vreg]                 (plain reload, no +0)
+    OP_COPYG,      // acc = G[buf]
+    OP_DIVC,       // acc = acc / p0                (collect_and_average divisor, node.rs:189-191)
+    OP_SAVEV,      // V[vreg] = acc
+    OP_STOREG,     // G[buf] = acc
+    OP_MODMAP,     // acc = p0 + (p1-p0)*clamp((acc+1)/2,0,1)   (lib.rs:138-146)
+    OP_GAIN,       // acc = acc * P0
+    OP_DISTORT,    // mode in `mode`; level P0      (nodes/distort.rs)
+    OP_OVERDRIVE,  // boost P0, drive P1, level P2  (nodes/overdrive.rs:31-43)
+    OP_CHEBY,      // p0 level_pos, p1 level_neg, p2 tanh(level_pos), p3 tanh(level_neg)
+    OP_ADD,        // acc = acc + V[vreg]           (nodes/add.rs: a + b, acc = a)
+    OP_MIX,        // acc = V[vreg]*r + acc*(1-r), r = P0 (nodes/mix.rs:45; acc = a, vreg = b)
+    OP_COMB,       // acc = acc + ring*p0 ; ring = acc      (nodes/reverb.rs:87-103), ring index `aux`
+    OP_BIQUAD,     // exact DF1, coefs p0..p4 = b0,b1,b2,a1,a2; state slot `aux`
+    OP_LP1,        // y = x*p1 + p0*z ; z = y  (p0 = ratio, p1 = 1-ratio), state slot `aux`
+    OP_HP1,        // z = x*p1 + p0*z ; y = x - z
+    OP_ENVELOPE,   // p0 attack gain, p1 release gain, state slot `aux`
+    OP_SIGGEN,     // mode; amplitude P0, frequency P1; p2 = sample rate; state slot `aux`
+};
+
+// Parameter source flags: bit i set => parameter Pi is a per-sample tile read from vreg pv[i]
+// (a connected `as_input` control port), else the scalar p[i].
+struct Op {
+    uint8_t code;
+    uint8_t mode;
+    uint8_t pflags;
+    uint8_t vreg;     // operand vreg for LOADV/ADDV/SAVEV/ADD/MIX
+    uint8_t pv[3];    // vregs of tile-valued parameters
+    uint8_t buf;      // global buffer index for LOADG/ADDG/STOREG, prefetch slot + 1 in `aux`
+    uint16_t aux;     // ring / state slot, or prefetch slot (0 = none, k+1 = slot k)
+    uint16_t pad;
+    float p[6];
+};
+
+struct BufDesc {       // a [C x n] f32 array in global memory
+    float* base;       // element (channel 0, sample 0 of this call)
+    int64_t row_stride;
+};
+
+struct RingDesc {      // Reverb ring, [C x D] f32
+    float* base;
+    int64_t D;         // delay length in samples (bit-exact index work)
+    int64_t pos;       // slot of this call's sample 0
+};
+
+struct Program {
+    int32_t n_ops;
+    int32_t n_vregs;       // shared-memory vregs (16 KB each); vreg ids >= n_vregs do not exist
+    int32_t n_prefetch;    // cp.async staging slots in use
+    int32_t needs_tile;    // program has lane=channel recurrences (transposition tile in smem)
+    Op ops[kMaxOps];
+    BufDesc bufs[kMaxBufs];
+    RingDesc rings[kMaxRings];
+    float* states[kMaxStates];  // [C x 4] f32 per stateful op
+    // prefetch slot k stages global buffer pf_buf[k] (>=0) or ring pf_ring[k] (>=0)
+    int16_t pf_buf[kMaxPrefetch];
+    int16_t pf_ring[kMaxPrefetch];
+};
+
+// ---- launchers (defined in the .cu files) -----------------------------------------------------------
+// Runs `prog` for channels [c_begin, c_end) and samples [0, T) of this call.  G in {1,2,4,8,16,32}.
+int launch_fused(const Program& prog, int G, int c_begin, int c_end, int64_t T, void* stream);
+int fused_smem_bytes(const Program& prog, int G);
+
+enum FirMode { FIR_FFT = 0, FIR_DIRECT = 1 };
+struct FirPlan {
+    int mode;             // FIR_FFT: overlap-save FFT (f32); FIR_DIRECT: time domain, f64, reference summation order
+    int log2F;            // FFT size F = 1 << log2F complex points, two channels per transform
+    int n_taps;           // N
+    int hist_pad;         // leading samples kept in U before this call's sample 0 (>= N-1, multiple of 4)
+    const float2* H;      // [F] spectrum of h in the transform's own output order, pre-scaled by 1/F
+    const double* taps;   // [N] reversed taps (f64) for the warm-up path
+    float divisor;        // 1/N (Average) or 1 (Balanced), fir.rs:187-190
+};
+// U: [C x (hist_pad + T)] input incl. history; Y: [C x T] output.  started = samples seen before this call.
+int launch_fir(const FirPlan& fp, const float* U, int64_t u_stride, float* Y, int64_t y_stride, int c_begin, int c_end,
+               int64_t T, int64_t started, void* stream, int* n_launches);
+// Computes H from taps on the device (f64 transform, same digit order as the f32 kernel).
+int fir_prepare_spectrum(int log2F, const double* taps_rev_host, int n_taps, float2* H_dev, void* stream);
+
+}  // namespace dspb

@@ -57,10 +57,12 @@ typedef struct dspb_config {
     int32_t ref_block;    /* 0 -> 128; Distort::Fuzz and SignalGen are evaluated per ref_block */
     int32_t ring_granule; /* 0 -> 1024.  Reverb ring capacity is rounded up to this many samples
                              (rivulet@b2416e5 page-mirrored ring; UNPINNED).  1 = nominal */
-    int32_t device;       /* CUDA device ordinal */
+    int32_t device;       /* CUDA device ordinal; -1 = planning only (dspb_compile / dspb_describe_plan work
+                             without a GPU, dspb_process fails with DSPB_ERR_CUDA) */
     int64_t max_samples;  /* largest n_samples a single dspb_process call will pass; 0 -> 64*block */
     int32_t fir_fft_log2; /* 0 -> engine default (13); FFT size of the overlap-save FIR path */
-    int32_t reserved;
+    int32_t fir_mode;     /* 0 -> overlap-save FFT in f32 (throughput path); 1 -> direct time-domain sum in f64 in
+                             the reference's summation order (bit-exact; 8192 f64 flop/sample at 4096 taps) */
 } dspb_config;
 
 /* ---- lifetime ----------------------------------------------------------------------------- */
