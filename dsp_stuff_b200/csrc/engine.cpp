@@ -211,6 +211,34 @@ int port_index(const std::vector<const char*>& v, const char* name) {
 
 int64_t round_up(int64_t n, int64_t g) { return g <= 1 ? n : (n + g - 1) / g * g; }
 
+// Host side of exact_math.cuh's div_const.  The 3-instruction sequence is NOT exact for every divisor
+// (measured: 0.3, 29.99, ... have millions of wrong quotients), so a divisor gets the fast path only
+// after the device has enumerated all 2^32 dividends against IEEE division with zero mismatches
+// (verify_const_div, a few ms, cached per process).  Everything else takes __fdiv_rn.
+bool div_const_ok(float b) {
+    if (!(b > 0.0f) || !std::isfinite(b) || b < 1e-30f || b > 1e30f) return false;
+    static std::map<uint32_t, bool> cache;
+    uint32_t bits;
+    memcpy(&bits, &b, 4);
+    auto it = cache.find(bits);
+    if (it != cache.end()) return it->second;
+    bool ok = false;
+    if (g_plan_only) {
+        ok = true;  // nothing runs in planning-only mode; show the optimistic schedule
+    } else {
+        unsigned long long mism = 1;
+        if (verify_const_div(b, 1.0f / b, &mism) == 0) ok = mism == 0;
+        cache[bits] = ok;
+    }
+    return ok;
+}
+void set_const_div(Op& op, int p_b, int p_r, float b) {
+    const bool ok = div_const_ok(b);
+    op.p[p_b] = b;
+    op.p[p_r] = ok ? 1.0f / b : 0.0f;
+    op.pad = ok ? 1 : 0;
+}
+
 // Reverb::refresh_seconds, nodes/reverb.rs:55-71.  Integer work: must match the reference exactly.
 int64_t reverb_delay(float seconds, int sample_rate, int granule) {
     float prod = seconds * (float)sample_rate;
@@ -320,7 +348,7 @@ struct Lowerer {
             first = false;
         }
         Op d = mk(OP_DIVC);
-        d.p[0] = nf;
+        set_const_div(d, 0, 1, nf);
         char b[96];
         snprintf(b, sizeof b, "acc /= %.9g           ; fan-in average of %zu link(s)", nf, ls.size());
         emit(d, b);
@@ -385,6 +413,39 @@ int Lowerer::finish_vregs(Step& st, std::vector<Op>& o, std::vector<std::string>
             }
         }
         i++;
+    }
+    // fold the fan-in prologue ("acc = 0.0 + acc", "acc /= nf") into the op that consumes it
+    auto consumes_acc = [](int c) {
+        return c == OP_GAIN || c == OP_DISTORT || c == OP_OVERDRIVE || c == OP_CHEBY || c == OP_COMB || c == OP_BIQUAD ||
+               c == OP_LP1 || c == OP_HP1 || c == OP_ENVELOPE || c == OP_STOREG || c == OP_SAVEV || c == OP_MODMAP ||
+               c == OP_ADD || c == OP_MIX;
+    };
+    for (size_t i = 0; i < o.size(); i++) {
+        int pre = 0;
+        size_t k = i;
+        if (o[k].code == OP_LOADV && o[k].vreg == 0xFF) { pre |= 1; k++; }
+        if (k < o.size() && o[k].code == OP_DIVC) {
+            pre |= 2 | (o[k].pad ? 4 : 0);
+            const float nf = o[k].p[0], r = o[k].p[1];
+            k++;
+            Op host;
+            std::string host_txt;
+            if (k < o.size() && consumes_acc(o[k].code) && o[k].pre == 0) { host = o[k]; host_txt = t[k]; k++; }
+            else { host = mk(OP_NOP); host_txt = "(fan-in prologue only)"; }
+            host.pre = (uint8_t)pre;
+            host.p[4] = nf;
+            host.p[5] = r;
+            char b[64];
+            snprintf(b, sizeof b, "[%sacc /= %.9g] ", (pre & 1) ? "acc = 0.0 + acc; " : "", nf);
+            o[i] = host;
+            t[i] = std::string(b) + host_txt;
+            o.erase(o.begin() + i + 1, o.begin() + k);
+            t.erase(t.begin() + i + 1, t.begin() + k);
+        } else if (pre) {  // "acc = 0.0 + acc" without a division cannot occur; keep it as a NOP prologue
+            Op host = mk(OP_NOP);
+            host.pre = 1;
+            o[i] = host;
+        }
     }
     // liveness
     std::map<int, std::pair<int, int>> live;  // virtual id -> [def, last use]
@@ -634,6 +695,7 @@ int Lowerer::lower() {
                         op.code = OP_DISTORT;
                         op.mode = (uint8_t)nd.enums[0];
                         ctl_param(op, 0, 0);
+                        set_const_div(op, 0, 1, nd.f32[0]);
                         snprintf(b, sizeof b, "acc = distort[%s](acc, %g)", nt.enums[0].variants[nd.enums[0]], nd.f32[0]);
                         break;
                     case T_OVERDRIVE:
@@ -653,7 +715,8 @@ int Lowerer::lower() {
                         break;
                     case T_BIQUAD:
                         op.code = OP_BIQUAD;
-                        for (int i = 0; i < 5; i++) op.p[i] = nd.bq[i];
+                        for (int i = 0; i < 4; i++) op.p[i] = nd.bq[i];
+                        op.a2 = nd.bq[4];
                         snprintf(b, sizeof b, "acc = DF1(acc; b=%g,%g,%g a=%g,%g) exact, lane=channel", nd.bq[0], nd.bq[1], nd.bq[2], nd.bq[3], nd.bq[4]);
                         break;
                     case T_LOWPASS:
@@ -711,7 +774,6 @@ int ensure_resources(dspb_engine* e) {
         if (n.type == T_FIR && (n.fir_dirty || !n.Y.p)) {
             const int N = (int)n.taps.size();
             const int F = 1 << e->cfg.fir_fft_log2;
-            if (N > F / 2) return fail(DSPB_ERR_INVALID, "fir: %d taps need fir_fft_log2 > %d", N, e->cfg.fir_fft_log2);
             n.hist_pad = (int)round_up(std::max(N - 1, 4), 4);
             for (auto& u : n.U) {
                 int r = u.alloc((size_t)C * (n.hist_pad + maxn) * 4, true);
@@ -725,8 +787,10 @@ int ensure_resources(dspb_engine* e) {
             if (r) return r;
             if (!e->plan_only) {
                 CUDA_TRY(cudaMemcpy(n.taps_dev.p, n.taps.data(), (size_t)N * 8, cudaMemcpyHostToDevice));
-                int rc = fir_prepare_spectrum(e->cfg.fir_fft_log2, n.taps.data(), N, reinterpret_cast<float2*>(n.H.p), nullptr);
-                if (rc) return fail(DSPB_ERR_CUDA, "fir_prepare_spectrum: %s", cudaGetErrorString((cudaError_t)rc));
+                if (N <= fir_fft_max_taps()) {  // longer impulse responses run on the exact direct path
+                    int rc = fir_prepare_spectrum(e->cfg.fir_fft_log2, reinterpret_cast<const double*>(n.taps_dev.p), N, reinterpret_cast<float2*>(n.H.p), nullptr);
+                    if (rc) return fail(DSPB_ERR_CUDA, "fir_prepare_spectrum: %s", cudaGetErrorString((cudaError_t)rc));
+                }
                 CUDA_TRY(cudaDeviceSynchronize());
             }
             n.started = 0;
@@ -837,7 +901,7 @@ int run_steps(dspb_engine* e, const float* const* d_in, float* const* d_out, int
         } else {
             Node& f = *e->nodes[s.fir_node];
             FirPlan fp;
-            fp.mode = e->cfg.fir_mode;
+            fp.mode = (int)f.taps.size() > fir_fft_max_taps() ? (int)FIR_DIRECT : e->cfg.fir_mode;  // long IRs: exact path
             fp.log2F = e->cfg.fir_fft_log2;
             fp.n_taps = (int)f.taps.size();
             fp.hist_pad = f.hist_pad;

@@ -5,26 +5,25 @@
 // loop + SimpleNode::process bodies (dsp-stuff/src/node.rs:267-352, nodes/*.rs).
 //
 // Geometry: a CTA owns G channels for the whole call and walks time in tiles of S = 4096/G samples,
-// so every sequential dependency (IIR state, comb ring, Fuzz/SignalGen 128-sample blocks) stays
-// inside one CTA.  256 threads; thread (g, j) holds 16 consecutive samples of channel g in
-// registers (`acc`).  HBM traffic is 128-bit per thread (4 x LDG/STG.128 per 16 samples); the next
-// tile's inputs and ring reads are prefetched with cp.async into shared memory while the current
-// tile computes.  Recurrences are executed lane = channel, strictly in time order with FMA-free
-// f32 arithmetic (bit-identical to the reference), after a conflict-free shared-memory transpose.
+// so every sequential dependency (IIR state, comb ring, Fuzz 128-sample blocks) stays inside one
+// CTA.  256 threads; thread (g, j) holds 16 consecutive samples of channel g in registers (`acc`).
+// HBM traffic is 128-bit per thread (4 x 16 B per 16 samples); the next tile's input and ring reads
+// are prefetched with cp.async into thread-private shared-memory staging right after the current
+// tile has consumed them, so they are in flight while the tile computes.
 //
-// Arithmetic that must match the reference bit for bit uses __fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn
-// so nvcc can never contract it into FMAs (rustc does not).
+// Recurrences (biquad / one-pole / envelope) are bit-identical to the reference: everything that
+// does not depend on the previous OUTPUT (the feed-forward taps) is computed time-parallel with the
+// reference's operation order, then one warp runs the remaining 2-4 dependent f32 ops per sample
+// lane = channel, strictly in time order, on a conflict-free transposed tile in shared memory.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
+#include "exact_math.cuh"
 #include "plan.h"
 
 namespace dspb {
 namespace {
-
-__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
-__device__ __forceinline__ float dv(float a, float b) { return __fdiv_rn(a, b); }
 
 // distort.rs:53-61
 __device__ __forceinline__ float clipf(float s) { return s < -1.0f ? -1.0f : (s > 1.0f ? 1.0f : s); }
@@ -34,7 +33,8 @@ __device__ __forceinline__ float clamp01(float x) { return x < 0.0f ? 0.0f : (x 
 
 enum DistortMode { HardClip, SoftClip, Tanh, RecipSoftClip, Fuzz, Sin, Atan, Square, Chebyshev4 };
 
-__device__ __forceinline__ float shape(int mode, float x, float l) {
+// Per-sample level (control port connected): kept out of line so the rare path costs no registers.
+__device__ __noinline__ float shape_generic(int mode, float x, float l) {
     if (l < 0.001f) return x;
     switch (mode) {
         case HardClip: return dv(clipf(mul(x, l)), l);
@@ -51,12 +51,19 @@ __device__ __forceinline__ float shape(int mode, float x, float l) {
         case Atan: return atanf(mul(x, l));
         case Square: { float v = mul(x, l); return mul(mul(v, v), signumf(v)); }
         case Chebyshev4: {
-            float v = mul(x, l);
-            float v2 = mul(v, v);
+            float v2 = mul(x, l);
+            v2 = mul(v2, v2);
             return add(sub(mul(8.0f, mul(v2, v2)), mul(8.0f, v2)), 1.0f);
         }
     }
     return x;
+}
+__device__ __noinline__ float overdrive_generic(float x, float b, float dr, float l) {  // overdrive.rs:31-43
+    if (l < 0.001f) return x;
+    const float FRAC_PI_4 = 0.785398163397448309615660845819875721f;
+    const float FRAC_2_PI = 0.636619772367581343075535053490057448f;
+    float d = mul(FRAC_2_PI, atanf(mul(FRAC_PI_4, mul(x, b))));
+    return mul(add(mul(dr, d), mul(sub(1.0f, dr), x)), l);
 }
 
 // max over the 8 consecutive threads (= one 128-sample reference block) of |v| under
@@ -76,8 +83,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     float4 r;
@@ -88,35 +94,28 @@ __device__ __forceinline__ void stg_stream(float4* p, float4 v) {
     asm volatile("st.global.cg.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-struct DF1 {  // crate biquad 0.4.2 DirectForm1<f32>::run via nodes/biquad.rs:87
-    float b0, b1, b2, a1, a2;
-    float x1, x2, y1, y2;
-    __device__ __forceinline__ void load(const float4 s) { x1 = s.x; x2 = s.y; y1 = s.z; y2 = s.w; }
-    __device__ __forceinline__ float4 save() const { return make_float4(x1, x2, y1, y2); }
-    __device__ __forceinline__ float step(float x) {
-        float out = sub(sub(add(add(mul(b0, x), mul(b1, x1)), mul(b2, x2)), mul(a1, y1)), mul(a2, y2));
-        x2 = x1; x1 = x; y2 = y1; y1 = out;
+// ---- sequential cores: only the ops that depend on the previous output ---------------------------------
+struct DF1Core {  // y = (p - a1*y1) - a2*y2, p = b0*x + b1*x1 + b2*x2 precomputed (biquad 0.4.2 DirectForm1::run)
+    float a1, a2, y1, y2;
+    __device__ __forceinline__ void load(const float4 s) { y1 = s.z; y2 = s.w; }
+    __device__ __forceinline__ void save(float4& s) const { s.z = y1; s.w = y2; }
+    __device__ __forceinline__ float step(float p) {
+        float out = sub(sub(p, mul(a1, y1)), mul(a2, y2));
+        y2 = y1; y1 = out;
         return out;
     }
 };
-struct LP1 {  // nodes/low_pass.rs:36-39
-    float r, omr, z;
+struct OnePoleCore {  // z = xr + r*z, xr = x*(1-r) precomputed (nodes/low_pass.rs:37, high_pass.rs:37)
+    float r, z;
     __device__ __forceinline__ void load(const float4 s) { z = s.x; }
-    __device__ __forceinline__ float4 save() const { return make_float4(z, 0.f, 0.f, 0.f); }
-    __device__ __forceinline__ float step(float x) { z = add(mul(x, omr), mul(r, z)); return z; }
+    __device__ __forceinline__ void save(float4& s) const { s.x = z; }
+    __device__ __forceinline__ float step(float xr) { z = add(xr, mul(r, z)); return z; }
 };
-struct HP1 {  // nodes/high_pass.rs:36-39
-    float r, omr, z;
-    __device__ __forceinline__ void load(const float4 s) { z = s.x; }
-    __device__ __forceinline__ float4 save() const { return make_float4(z, 0.f, 0.f, 0.f); }
-    __device__ __forceinline__ float step(float x) { z = add(mul(x, omr), mul(r, z)); return sub(x, z); }
-};
-struct Env {  // dasp_envelope 0.11.0 Detector<f32, Peak<FullWave>>::next via nodes/envelope.rs:50
+struct EnvCore {  // dasp_envelope 0.11.0 Detector<f32, Peak<FullWave>>::next, d = |x| precomputed
     float ga, gr, prev;
     __device__ __forceinline__ void load(const float4 s) { prev = s.x; }
-    __device__ __forceinline__ float4 save() const { return make_float4(prev, 0.f, 0.f, 0.f); }
-    __device__ __forceinline__ float step(float x) {
-        float d = fabsf(x);
+    __device__ __forceinline__ void save(float4& s) const { s.x = prev; }
+    __device__ __forceinline__ float step(float d) {
         float g = prev < d ? ga : gr;
         prev = add(d, mul(sub(prev, d), g));
         return prev;
@@ -124,8 +123,8 @@ struct Env {  // dasp_envelope 0.11.0 Detector<f32, Peak<FullWave>>::next via no
 };
 
 // Swizzled float4 slot of logical float4 index m inside a tile row: thread j writes its four
-// float4s to 4j + (k ^ ((j>>1)&3)), which makes both the time-parallel writes (8 lanes, stride 64 B)
-// and the lane = channel reads (rows padded by 4 floats) bank-conflict free.
+// float4s to 4j + (k ^ ((j>>1)&3)), which makes both the time-parallel accesses (8 lanes, stride 64 B)
+// and the lane = channel accesses (rows padded by 4 floats) bank-conflict free.
 __device__ __forceinline__ int swz(int m) { return (m & ~3) | ((m & 3) ^ ((m >> 3) & 3)); }
 
 template <int G>
@@ -135,368 +134,611 @@ struct Geo {
     static constexpr int ROW = S + 4;          // padded tile row (floats)
 };
 
-template <int G, class R>
-__device__ __forceinline__ void run_recurrence(R rec, float (&acc)[kChunk], float* tile, float4* sm_state,
-                                               int g, int j, int valid_f4) {
+struct TileCtx {
+    float* tile;
+    int g, j, valid_f4, rec_warp;
+};
+
+// v (time-parallel, 16 per thread) -> tile; one warp runs `core` lane = channel; tile -> v.
+template <int G, class Core>
+__device__ __forceinline__ void run_recurrence(Core core, float (&v)[kChunk], const TileCtx& c, float4* st) {
     using Q = Geo<G>;
-    const int t = threadIdx.x;
-    float4* row = reinterpret_cast<float4*>(tile + g * Q::ROW);
+    float4* row = reinterpret_cast<float4*>(c.tile + c.g * Q::ROW);
 #pragma unroll
     for (int k = 0; k < 4; k++)
-        row[4 * j + (k ^ ((j >> 1) & 3))] = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+        row[4 * c.j + (k ^ ((c.j >> 1) & 3))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
     __syncthreads();
-    if (t < G && valid_f4 > 0) {  // lane = channel, strictly sequential in time
-        float4* r = reinterpret_cast<float4*>(tile + t * Q::ROW);
-        rec.load(sm_state[t]);
-        float4 v = r[swz(0)];
-        for (int m = 0; m < valid_f4; m++) {
-            float4 nx = v;
-            if (m + 1 < valid_f4) nx = r[swz(m + 1)];
-            v.x = rec.step(v.x);
-            v.y = rec.step(v.y);
-            v.z = rec.step(v.z);
-            v.w = rec.step(v.w);
-            r[swz(m)] = v;
-            v = nx;
+    const int lane = threadIdx.x & 31;
+    if ((threadIdx.x >> 5) == c.rec_warp && lane < G && c.valid_f4 > 0) {  // strictly sequential in time
+        float4* r = reinterpret_cast<float4*>(c.tile + lane * Q::ROW);
+        float4 s = st[lane];
+        core.load(s);
+        float4 x = r[swz(0)];
+        for (int m = 0; m < c.valid_f4; m++) {
+            float4 nx = x;
+            if (m + 1 < c.valid_f4) nx = r[swz(m + 1)];
+            x.x = core.step(x.x);
+            x.y = core.step(x.y);
+            x.z = core.step(x.z);
+            x.w = core.step(x.w);
+            r[swz(m)] = x;
+            x = nx;
         }
-        sm_state[t] = rec.save();
+        core.save(s);
+        st[lane] = s;
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        float4 v = row[4 * j + (k ^ ((j >> 1) & 3))];
-        acc[4 * k] = v.x; acc[4 * k + 1] = v.y; acc[4 * k + 2] = v.z; acc[4 * k + 3] = v.w;
+        float4 q = row[4 * c.j + (k ^ ((c.j >> 1) & 3))];
+        v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
     }
 }
 
-template <int G>
-__global__ void __launch_bounds__(kThreads, 2)
-fused_kernel(const __grid_constant__ Program prog, int c_begin, int c_end, long long T, int n_states) {
-    using Q = Geo<G>;
-    extern __shared__ float4 smem4[];
-    const int t = threadIdx.x;
-    const int g = t / Q::TPC;
-    const int j = t % Q::TPC;
-    const int ch = c_begin + blockIdx.x * G + g;
-    const bool ch_ok = ch < c_end;
-
-    // shared memory carve-up
-    float4* sm_state = smem4;                                  // [kMaxStates][G]
-    float* tile = reinterpret_cast<float*>(sm_state + kMaxStates * G);
-    float4* stage = reinterpret_cast<float4*>(tile + (prog.needs_tile ? G * Q::ROW : 0));  // [2][n_prefetch][4][256]
-    float4* vregs = stage + 2 * prog.n_prefetch * 4 * kThreads;  // [n_vregs][4][256]
-
-    for (int i = t; i < n_states * G; i += kThreads) {
-        int s = i / G, c = c_begin + blockIdx.x * G + (i % G);
-        sm_state[s * G + (i % G)] = c < c_end ? reinterpret_cast<const float4*>(prog.states[s])[c] : make_float4(0, 0, 0, 0);
+__device__ __forceinline__ void load16(const float4* s, int stride, float (&v)[kChunk]) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        float4 q = s[k * stride];
+        v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
     }
-
-    const long long n_tiles = (T + Q::S - 1) / Q::S;
-    const bool fast_ring_all = true;
-    (void)fast_ring_all;
-
-    auto issue_prefetch = [&](long long tile_i, int parity) {
-        const long long n0 = tile_i * Q::S + (long long)j * kChunk;
-        if (ch_ok && tile_i < n_tiles && n0 < T) {
+}
+__device__ __forceinline__ void store16(float4* s, int stride, const float (&v)[kChunk]) {
 #pragma unroll
-            for (int s = 0; s < kMaxPrefetch; s++) {
-                if (s >= prog.n_prefetch) break;
-                const float* src;
-                if (prog.pf_buf[s] >= 0) {
-                    const BufDesc& b = prog.bufs[prog.pf_buf[s]];
-                    src = b.base + (long long)ch * b.row_stride + n0;
-                } else {
-                    const RingDesc& r = prog.rings[prog.pf_ring[s]];
-                    src = r.base + (long long)ch * r.D + (r.pos + n0) % r.D;
-                }
-                float4* dst = stage + ((parity * prog.n_prefetch + s) * 4) * kThreads + t;
+    for (int k = 0; k < 4; k++) s[k * stride] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+}
+
+// acc[i] /= b for a host-known divisor: exact fast path, IEEE division when the chunk holds zeros,
+// denormal-range or huge values (exact_math.cuh)
+__device__ __forceinline__ void div16(float (&acc)[kChunk], const ConstDiv d, bool use_fast) {
+    if (use_fast) {
+        float q[kChunk];
+        float mn = kDivHi, mx = 0.0f;
 #pragma unroll
-                for (int k = 0; k < 4; k++) cp_async16(dst + k * kThreads, src + 4 * k);
+        for (int i = 0; i < kChunk; i++) q[i] = div_const(acc[i], d, mn, mx);
+        if (div_const_accept(mn, mx)) {
+#pragma unroll
+            for (int i = 0; i < kChunk; i++) acc[i] = q[i];
+            return;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < kChunk; i++) acc[i] = dv(acc[i], d.b);
+}
+
+// Per-CTA / per-tile context shared by every op.
+template <int G>
+struct Ctx {
+    const Program* prog;
+    float4* sm_state;
+    float2* edge;
+    float4* stage;
+    float4* vregs;
+    TileCtx tc;
+    long long n0, tile_i, n_tiles, T;
+    int t, g, j, ch, j_last;
+    bool ch_ok, active;
+
+    // stage slot s for tile `ti` (thread-private, so no barrier is needed around it)
+    __device__ __forceinline__ void issue_prefetch(int s, long long ti) const {
+        using Q = Geo<G>;
+        const long long m0 = ti * Q::S + (long long)j * kChunk;
+        if (ch_ok && ti < n_tiles && m0 < T) {
+            const float* src;
+            if (prog->pf_buf[s] >= 0) {
+                const BufDesc& b = prog->bufs[prog->pf_buf[s]];
+                src = b.base + (long long)ch * b.row_stride + m0;
+            } else {
+                const RingDesc& r = prog->rings[prog->pf_ring[s]];
+                src = r.base + (long long)ch * r.D + (r.pos + m0) % r.D;
             }
+            float4* dst = stage + (s * 4) * kThreads + t;
+#pragma unroll
+            for (int k = 0; k < 4; k++) cp_async16(dst + k * kThreads, src + 4 * k);
         }
         cp_async_commit();
-    };
+    }
+};
 
-    issue_prefetch(0, 0);
+// One op of the segment program on this thread's 16 samples.  `code`, `mode` and `pre` are
+// compile-time constants in the specialised kernels (the switch folds away) and run-time values in
+// the generic interpreter.  pre & 1: acc = 0.0 + acc (first link of a fan-in sum, node.rs:181-183);
+// pre & 2: acc /= nf (node.rs:189-191) with the divisor in p[4], its reciprocal in p[5].
+template <int G>
+__device__ __forceinline__ void exec_op(const int code, const int mode, const int pre, const Op& op, const Ctx<G>& c,
+                                        float (&acc)[kChunk]) {
+    const Program& prog = *c.prog;
+    const int t = c.t;
+    if (pre & 1) {
+#pragma unroll
+        for (int i = 0; i < kChunk; i++) acc[i] = add(0.0f, acc[i]);
+    }
+    if (pre & 2) div16(acc, ConstDiv{op.p[4], op.p[5]}, pre & 4);
+    switch (code) {
+        case OP_NOP: break;
+        case OP_ZERO: {
+#pragma unroll
+            for (int i = 0; i < kChunk; i++) acc[i] = 0.0f;
+        } break;
+        case OP_LOADG:
+        case OP_ADDG:
+        case OP_COPYG: {
+            float v[kChunk];
+#pragma unroll
+            for (int i = 0; i < kChunk; i++) v[i] = 0.0f;
+            if (op.aux) {  // staged by cp.async; refill the slot for the next tile right away
+                if (c.active) load16(c.stage + ((op.aux - 1) * 4) * kThreads + t, kThreads, v);
+                c.issue_prefetch(op.aux - 1, c.tile_i + 1);
+            } else if (c.active) {
+                const BufDesc& b = prog.bufs[op.buf];
+                const float4* p = reinterpret_cast<const float4*>(b.base + (long long)c.ch * b.row_stride + c.n0);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    float4 q = ldg_stream(p + k);
+                    v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kChunk; i++)
+                acc[i] = code == OP_COPYG ? v[i] : add(code == OP_LOADG ? 0.0f : acc[i], v[i]);
+        } break;
+        case OP_LOADV:
+        case OP_ADDV:
+        case OP_COPYV:
+        case OP_ADD: {
+            float v[kChunk];
+            load16(c.vregs + (op.vreg * 4) * kThreads + t, kThreads, v);
+#pragma unroll
+            for (int i = 0; i < kChunk; i++)
+                acc[i] = code == OP_COPYV ? v[i] : add(code == OP_LOADV ? 0.0f : acc[i], v[i]);
+        } break;
+        case OP_SAVEV: {
+            store16(c.vregs + (op.vreg * 4) * kThreads + t, kThreads, acc);
+        } break;
+        case OP_STOREG: {
+            if (c.active) {
+                const BufDesc& b = prog.bufs[op.buf];
+                float4* p = reinterpret_cast<float4*>(b.base + (long long)c.ch * b.row_stride + c.n0);
+#pragma unroll
+                for (int k = 0; k < 4; k++) stg_stream(p + k, make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]));
+            }
+        } break;
+        case OP_MODMAP: {  // lib.rs:138-146; (x + 1) / 2 == (x + 1) * 0.5 exactly
+            const float lo = op.p[0], span = sub(op.p[1], op.p[0]);
+#pragma unroll
+            for (int i = 0; i < kChunk; i++) acc[i] = add(lo, mul(span, clamp01(mul(add(acc[i], 1.0f), 0.5f))));
+        } break;
+        case OP_GAIN: {
+            if (op.pflags & 1) {
+                float P[kChunk];
+                load16(c.vregs + (op.pv[0] * 4) * kThreads + t, kThreads, P);
+#pragma unroll
+                for (int i = 0; i < kChunk; i++) acc[i] = mul(acc[i], P[i]);
+            } else {
+                const float l = op.p[0];
+#pragma unroll
+                for (int i = 0; i < kChunk; i++) acc[i] = mul(acc[i], l);
+            }
+        } break;
+        case OP_DISTORT: {
+            if (!(op.pflags & 1) && mode != Fuzz) {  // scalar level: the common case
+                const float l = op.p[0];
+                if (l < 0.001f) break;  // every shaper returns the sample unchanged (distort.rs:64,...)
+                const ConstDiv dl{l, op.p[1]};
+                const bool fast = op.pad & 1;
+                switch (mode) {
+                    case HardClip: {
+#pragma unroll
+                        for (int i = 0; i < kChunk; i++) acc[i] = clipf(mul(acc[i], l));
+                        div16(acc, dl, fast);
+                    } break;
+                    case SoftClip: {
+                        const ConstDiv d3{3.0f, 0.333333343267440796f};
+                        float c3[kChunk];
+#pragma unroll
+                        for (int i = 0; i < kChunk; i++) {
+                            acc[i] = mul(acc[i], l);
+                            c3[i] = mul(mul(acc[i], acc[i]), acc[i]);
+                        }
+                        div16(c3, d3, true);
+#pragma unroll
+                        for (int i = 0; i < kChunk; i++) {
+                            float s = acc[i];
+                            if (s > 1.0f) s = 2.0f / 3.0f;
+                            else if (s >= -1.0f && s <= 1.0f) s = sub(s, c3[i]);
+                            else s = -2.0f / 3.0f;
+                            acc[i] = clipf(s);
+                        }
+                        div16(acc, dl, fast);
+                    } break;
+                    case Tanh: {
+#pragma unroll
+                        for (int i = 0; i < kChunk; i++) acc[i] = tanhf(mul(acc[i], l));
+                    } break;
+                    case RecipSoftClip: {
+#pragma unroll
+                        for (int i = 0; i < kChunk; i++)
+                            acc[i] = mul(signumf(acc[i]), sub(1.0f, dv(1.0f, add(mul(fabsf(acc[i]), l), 1.0f))));
+                    } break;
+                    case Sin: {
+#pragma unroll
+                        for (int i = 0; i < kChunk; i++) acc[i] = sinf(mul(acc[i], l));
+                    } break;
+                    case Atan: {
+#pragma unroll
+                        for (int i = 0; i < kChunk; i++) acc[i] = atanf(mul(acc[i], l));
+                    } break;
+                    case Square: {
+#pragma unroll
+                        for (int i = 0; i < kChunk; i++) {
+                            float v = mul(acc[i], l);
+                            acc[i] = mul(mul(v, v), signumf(v));
+                        }
+                    } break;
+                    case Chebyshev4: {
+#pragma unroll
+                        for (int i = 0; i < kChunk; i++) {
+                            float v2 = mul(acc[i], l);
+                            v2 = mul(v2, v2);
+                            acc[i] = add(sub(mul(8.0f, mul(v2, v2)), mul(8.0f, v2)), 1.0f);
+                        }
+                    } break;
+                }
+                break;
+            }
+            float P[kChunk];
+            if (op.pflags & 1) load16(c.vregs + (op.pv[0] * 4) * kThreads + t, kThreads, P);
+            else {
+#pragma unroll
+                for (int i = 0; i < kChunk; i++) P[i] = op.p[0];
+            }
+            if (mode == Fuzz) {  // nodes/distort.rs:146-172, per 128-sample reference block
+                const float mx = block128_max_abs(acc);
+                float z[kChunk];
+#pragma unroll
+                for (int i = 0; i < kChunk; i++) {
+                    float q = dv(clipf(mul(acc[i], P[i])), mx);
+                    z[i] = copysignf(sub(1.0f, expf(copysignf(q, -1.0f))), -1.0f);
+                }
+                const float mz = block128_max_abs(z);
+#pragma unroll
+                for (int i = 0; i < kChunk; i++) z[i] = dv(clipf(mul(z[i], mx)), mz);
+                const float my = block128_max_abs(z);
+#pragma unroll
+                for (int i = 0; i < kChunk; i++) acc[i] = dv(mul(z[i], mx), my);
+            } else {  // per-sample level from a control port: generic path
+#pragma unroll
+                for (int i = 0; i < kChunk; i++) acc[i] = shape_generic(mode, acc[i], P[i]);
+            }
+        } break;
+        case OP_OVERDRIVE: {
+            if (op.pflags & 7) {
+                float B[kChunk], D[kChunk], L[kChunk];
+#pragma unroll
+                for (int i = 0; i < kChunk; i++) { B[i] = op.p[0]; D[i] = op.p[1]; L[i] = op.p[2]; }
+                if (op.pflags & 1) load16(c.vregs + (op.pv[0] * 4) * kThreads + t, kThreads, B);
+                if (op.pflags & 2) load16(c.vregs + (op.pv[1] * 4) * kThreads + t, kThreads, D);
+                if (op.pflags & 4) load16(c.vregs + (op.pv[2] * 4) * kThreads + t, kThreads, L);
+#pragma unroll
+                for (int i = 0; i < kChunk; i++) acc[i] = overdrive_generic(acc[i], B[i], D[i], L[i]);
+            } else {
+                const float FRAC_PI_4 = 0.785398163397448309615660845819875721f;
+                const float FRAC_2_PI = 0.636619772367581343075535053490057448f;
+                const float b = op.p[0], dr = op.p[1], l = op.p[2];
+                if (l < 0.001f) break;
+                const float omd = sub(1.0f, dr);
+#pragma unroll
+                for (int i = 0; i < kChunk; i++) {
+                    const float x = acc[i];
+                    float d = mul(FRAC_2_PI, atanf(mul(FRAC_PI_4, mul(x, b))));
+                    acc[i] = mul(add(mul(dr, d), mul(omd, x)), l);
+                }
+            }
+        } break;
+        case OP_CHEBY: {
+            const float lp = op.p[0], ln = op.p[1], tp = op.p[2], tn = op.p[3];
+#pragma unroll
+            for (int i = 0; i < kChunk; i++) {
+                const float x = acc[i];
+                if (x >= 0.0f) { if (!(lp < 0.001f)) acc[i] = dv(tanhf(mul(x, lp)), tp); }
+                else { if (!(ln < 0.001f)) acc[i] = dv(tanhf(mul(x, ln)), tn); }
+            }
+        } break;
+        case OP_MIX: {
+            float b[kChunk];
+            load16(c.vregs + (op.vreg * 4) * kThreads + t, kThreads, b);
+            if (op.pflags & 1) {
+                float R[kChunk];
+                load16(c.vregs + (op.pv[0] * 4) * kThreads + t, kThreads, R);
+#pragma unroll
+                for (int i = 0; i < kChunk; i++) acc[i] = add(mul(b[i], R[i]), mul(acc[i], sub(1.0f, R[i])));
+            } else {
+                const float r = op.p[0], omr = sub(1.0f, r);
+#pragma unroll
+                for (int i = 0; i < kChunk; i++) acc[i] = add(mul(b[i], r), mul(acc[i], omr));
+            }
+        } break;
+        case OP_COMB: {
+            const RingDesc& r = prog.rings[op.aux & 0xff];
+            const float decay = op.p[0];
+            const int pslot = op.aux >> 8;  // 0 = not staged
+            float* rrow = r.base + (long long)c.ch * r.D;
+            if ((r.D & 15) == 0 && (r.pos & 15) == 0) {
+                const long long slot = (r.pos + c.n0) % r.D;
+                float old[kChunk];
+#pragma unroll
+                for (int i = 0; i < kChunk; i++) old[i] = 0.0f;
+                if (pslot) {
+                    if (c.active) load16(c.stage + ((pslot - 1) * 4) * kThreads + t, kThreads, old);
+                    c.issue_prefetch(pslot - 1, c.tile_i + 1);
+                } else if (c.active) {
+                    const float4* p = reinterpret_cast<const float4*>(rrow + slot);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        float4 q = ldg_stream(p + k);
+                        old[4 * k] = q.x; old[4 * k + 1] = q.y; old[4 * k + 2] = q.z; old[4 * k + 3] = q.w;
+                    }
+                }
+                if (c.active) {
+#pragma unroll
+                    for (int i = 0; i < kChunk; i++) acc[i] = add(acc[i], mul(old[i], decay));
+                    float4* p = reinterpret_cast<float4*>(rrow + slot);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) stg_stream(p + k, make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]));
+                }
+            } else if (c.active) {  // ring length not a multiple of 16: element-wise wrap
+                long long slot = (r.pos + c.n0) % r.D;
+#pragma unroll
+                for (int i = 0; i < kChunk; i++) {
+                    float o = __ldcg(rrow + slot);
+                    acc[i] = add(acc[i], mul(o, decay));
+                    __stcg(rrow + slot, acc[i]);
+                    if (++slot == r.D) slot = 0;
+                }
+            }
+        } break;
+        case OP_BIQUAD: {
+            // p[n] = b0*x[n] + b1*x[n-1] + b2*x[n-2] in the reference's order, time-parallel
+            const float b0 = op.p[0], b1 = op.p[1], b2 = op.p[2];
+            float4* st = c.sm_state + op.aux * G;
+            c.edge[t] = make_float2(acc[14], acc[15]);
+            __syncthreads();
+            float xm1, xm2;
+            if (c.j == 0) { const float4 s = st[c.g]; xm1 = s.x; xm2 = s.y; }
+            else { const float2 e = c.edge[t - 1]; xm2 = e.x; xm1 = e.y; }
+            const float nx1 = acc[15], nx2 = acc[14];
+            float pm1 = acc[0], pm2;
+            acc[0] = add(add(mul(b0, acc[0]), mul(b1, xm1)), mul(b2, xm2));
+            pm2 = pm1; pm1 = acc[1];
+            acc[1] = add(add(mul(b0, acc[1]), mul(b1, pm2)), mul(b2, xm1));
+#pragma unroll
+            for (int i = 2; i < kChunk; i++) {
+                const float xi = acc[i];
+                acc[i] = add(add(mul(b0, xi), mul(b1, pm1)), mul(b2, pm2));
+                pm2 = pm1; pm1 = xi;
+            }
+            DF1Core core;
+            core.a1 = op.p[3];
+            core.a2 = op.a2;
+            run_recurrence<G>(core, acc, c.tc, st);  // first barrier inside: every thread has read st / edge
+            if (c.j == c.j_last) { st[c.g].x = nx1; st[c.g].y = nx2; }
+        } break;
+        case OP_LP1:
+        case OP_HP1: {
+            const float omr = op.p[1];
+            float v[kChunk];
+#pragma unroll
+            for (int i = 0; i < kChunk; i++) v[i] = mul(acc[i], omr);
+            OnePoleCore core;
+            core.r = op.p[0];
+            run_recurrence<G>(core, v, c.tc, c.sm_state + op.aux * G);
+#pragma unroll
+            for (int i = 0; i < kChunk; i++) acc[i] = code == OP_LP1 ? v[i] : sub(acc[i], v[i]);
+        } break;
+        case OP_ENVELOPE: {
+#pragma unroll
+            for (int i = 0; i < kChunk; i++) acc[i] = fabsf(acc[i]);
+            EnvCore core;
+            core.ga = op.p[0];
+            core.gr = op.p[1];
+            run_recurrence<G>(core, acc, c.tc, c.sm_state + op.aux * G);
+        } break;
+        default: break;
+    }
+}
+
+// Compile-time op signatures of the BASELINE chains: same exec_op code, opcodes constant-folded.
+// sig(i) packs code | mode << 8 | pre << 16; n = 0 selects the run-time interpreter.
+struct ChainDynamic { static constexpr int n = 0; __host__ __device__ static constexpr int sig(int) { return 0; } };
+#define DSPB_SIG(code, mode, pre) ((code) | ((mode) << 8) | ((pre) << 16))
+struct ChainGDBR {  // src -> gain -> distort(SoftClip) -> biquad -> reverb -> store   (config 3 / target front end)
+    static constexpr int n = 6;
+    __host__ __device__ static constexpr int sig(int i) {
+        return i == 0 ? DSPB_SIG(OP_LOADG, 0, 0) : i == 1 ? DSPB_SIG(OP_GAIN, 0, 6) : i == 2 ? DSPB_SIG(OP_DISTORT, SoftClip, 7)
+             : i == 3 ? DSPB_SIG(OP_BIQUAD, 0, 7) : i == 4 ? DSPB_SIG(OP_COMB, 0, 7) : DSPB_SIG(OP_STOREG, 0, 7);
+    }
+};
+struct ChainGDR {  // src -> gain -> distort(SoftClip) -> reverb -> store   (config 1)
+    static constexpr int n = 5;
+    __host__ __device__ static constexpr int sig(int i) {
+        return i == 0 ? DSPB_SIG(OP_LOADG, 0, 0) : i == 1 ? DSPB_SIG(OP_GAIN, 0, 6) : i == 2 ? DSPB_SIG(OP_DISTORT, SoftClip, 7)
+             : i == 3 ? DSPB_SIG(OP_COMB, 0, 7) : DSPB_SIG(OP_STOREG, 0, 7);
+    }
+};
+struct ChainBB {  // src -> biquad -> biquad -> store   (config 2)
+    static constexpr int n = 4;
+    __host__ __device__ static constexpr int sig(int i) {
+        return i == 0 ? DSPB_SIG(OP_LOADG, 0, 0) : i == 1 ? DSPB_SIG(OP_BIQUAD, 0, 6) : i == 2 ? DSPB_SIG(OP_BIQUAD, 0, 7) : DSPB_SIG(OP_STOREG, 0, 7);
+    }
+};
+struct ChainLH {  // src -> low_pass -> high_pass -> store   (config 2, one-pole variant)
+    static constexpr int n = 4;
+    __host__ __device__ static constexpr int sig(int i) {
+        return i == 0 ? DSPB_SIG(OP_LOADG, 0, 0) : i == 1 ? DSPB_SIG(OP_LP1, 0, 6) : i == 2 ? DSPB_SIG(OP_HP1, 0, 7) : DSPB_SIG(OP_STOREG, 0, 7);
+    }
+};
+struct ChainCopy {  // G -> (/nf) -> store   (the segment after a Fir node)
+    static constexpr int n = 2;
+    __host__ __device__ static constexpr int sig(int i) { return i == 0 ? DSPB_SIG(OP_LOADG, 0, 0) : DSPB_SIG(OP_STOREG, 0, 6); }
+};
+
+template <int G, class Chain, int I>
+__device__ __forceinline__ void run_static(const Program& prog, const Ctx<G>& c, float (&acc)[kChunk]) {
+    if constexpr (I < Chain::n) {
+        constexpr int s = Chain::sig(I);
+        exec_op<G>(s & 0xff, (s >> 8) & 0xff, (s >> 16) & 0xff, prog.ops[I], c, acc);
+        run_static<G, Chain, I + 1>(prog, c, acc);
+    }
+}
+
+template <int G, class Chain>
+__global__ void __launch_bounds__(kThreads, 3)
+fused_kernel(const __grid_constant__ Program prog, int c_begin, int c_end, long long T, int n_states, int n_sm) {
+    using Q = Geo<G>;
+    extern __shared__ float4 smem4[];
+    Ctx<G> c;
+    c.prog = &prog;
+    c.t = threadIdx.x;
+    c.g = c.t / Q::TPC;
+    c.j = c.t % Q::TPC;
+    c.ch = c_begin + blockIdx.x * G + c.g;
+    c.ch_ok = c.ch < c_end;
+    c.T = T;
+    const int t = c.t;
+
+    // shared memory carve-up
+    c.sm_state = smem4;                                                  // [kMaxStates][G]
+    c.edge = reinterpret_cast<float2*>(c.sm_state + kMaxStates * G);     // [256] chunk-edge samples
+    float* tile = reinterpret_cast<float*>(c.edge + kThreads);
+    c.stage = reinterpret_cast<float4*>(tile + (prog.needs_tile ? G * Q::ROW : 0));  // [n_prefetch][4][256]
+    c.vregs = c.stage + prog.n_prefetch * 4 * kThreads;                              // [n_vregs][4][256]
+
+    for (int i = t; i < n_states * G; i += kThreads) {
+        int s = i / G, cc = c_begin + blockIdx.x * G + (i % G);
+        c.sm_state[s * G + (i % G)] = cc < c_end ? reinterpret_cast<const float4*>(prog.states[s])[cc] : make_float4(0, 0, 0, 0);
+    }
+
+    c.n_tiles = (T + Q::S - 1) / Q::S;
+    c.tc.tile = tile;
+    c.tc.g = c.g;
+    c.tc.j = c.j;
+    // co-resident CTAs (bid, bid + n_sm, ...) put their sequential warp on different SM sub-partitions
+    c.tc.rec_warp = 7 - (int)((blockIdx.x / (unsigned)n_sm) & 3u);
+
+    for (int s = 0; s < prog.n_prefetch; s++) c.issue_prefetch(s, 0);
     __syncthreads();
 
-    for (long long tile_i = 0; tile_i < n_tiles; tile_i++) {
-        const int parity = (int)(tile_i & 1);
-        const long long n0 = tile_i * Q::S + (long long)j * kChunk;
-        const bool active = ch_ok && n0 < T;
+    for (long long tile_i = 0; tile_i < c.n_tiles; tile_i++) {
+        c.tile_i = tile_i;
+        c.n0 = tile_i * Q::S + (long long)c.j * kChunk;
+        c.active = c.ch_ok && c.n0 < T;
         const long long rem = T - tile_i * Q::S;
-        const int valid_f4 = (int)((rem < Q::S ? rem : Q::S) / 4);
+        c.tc.valid_f4 = (int)((rem < Q::S ? rem : Q::S) / 4);
+        c.j_last = c.tc.valid_f4 / 4 - 1;  // thread holding the last valid chunk of each channel
 
-        __syncthreads();  // ring / vreg / tile hazards across tiles
-        issue_prefetch(tile_i + 1, parity ^ 1);
-        cp_async_wait<1>();
+        __syncthreads();  // ring / tile hazards across tiles
+        cp_async_wait_all();
 
         float acc[kChunk];
 #pragma unroll
         for (int i = 0; i < kChunk; i++) acc[i] = 0.0f;
 
-        for (int ip = 0; ip < prog.n_ops; ip++) {
-            const Op& op = prog.ops[ip];
-            const int code = op.code;
-
-            // tile-valued parameters (connected control ports)
-            auto load_param = [&](int which, float (&P)[kChunk]) {
-                if (op.pflags & (1 << which)) {
-                    const float4* v = vregs + (op.pv[which] * 4) * kThreads + t;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        float4 q = v[k * kThreads];
-                        P[4 * k] = q.x; P[4 * k + 1] = q.y; P[4 * k + 2] = q.z; P[4 * k + 3] = q.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < kChunk; i++) P[i] = op.p[which];
-                }
-            };
-
-            switch (code) {
-                case OP_ZERO: {
-#pragma unroll
-                    for (int i = 0; i < kChunk; i++) acc[i] = 0.0f;
-                } break;
-                case OP_LOADG:
-                case OP_ADDG:
-                case OP_COPYG: {
-                    float v[kChunk];
-                    if (op.aux) {  // staged by cp.async
-                        const float4* s = stage + ((parity * prog.n_prefetch + (op.aux - 1)) * 4) * kThreads + t;
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            float4 q = s[k * kThreads];
-                            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
-                        }
-                    } else if (active) {
-                        const BufDesc& b = prog.bufs[op.buf];
-                        const float4* p = reinterpret_cast<const float4*>(b.base + (long long)ch * b.row_stride + n0);
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            float4 q = ldg_stream(p + k);
-                            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < kChunk; i++) v[i] = 0.0f;
-                    }
-                    if (!active) {
-#pragma unroll
-                        for (int i = 0; i < kChunk; i++) v[i] = 0.0f;
-                    }
-#pragma unroll
-                    for (int i = 0; i < kChunk; i++)
-                        acc[i] = code == OP_COPYG ? v[i] : add(code == OP_LOADG ? 0.0f : acc[i], v[i]);
-                } break;
-                case OP_LOADV:
-                case OP_ADDV:
-                case OP_COPYV:
-                case OP_ADD: {
-                    const float4* s = vregs + (op.vreg * 4) * kThreads + t;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        float4 q = s[k * kThreads];
-                        if (code == OP_COPYV) {
-                            acc[4 * k] = q.x; acc[4 * k + 1] = q.y; acc[4 * k + 2] = q.z; acc[4 * k + 3] = q.w;
-                        } else {
-                            const bool ld = code == OP_LOADV;
-                            acc[4 * k] = add(ld ? 0.0f : acc[4 * k], q.x);
-                            acc[4 * k + 1] = add(ld ? 0.0f : acc[4 * k + 1], q.y);
-                            acc[4 * k + 2] = add(ld ? 0.0f : acc[4 * k + 2], q.z);
-                            acc[4 * k + 3] = add(ld ? 0.0f : acc[4 * k + 3], q.w);
-                        }
-                    }
-                } break;
-                case OP_DIVC: {
-                    const float nf = op.p[0];
-#pragma unroll
-                    for (int i = 0; i < kChunk; i++) acc[i] = dv(acc[i], nf);
-                } break;
-                case OP_SAVEV: {
-                    float4* s = vregs + (op.vreg * 4) * kThreads + t;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) s[k * kThreads] = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
-                } break;
-                case OP_STOREG: {
-                    if (active) {
-                        const BufDesc& b = prog.bufs[op.buf];
-                        float4* p = reinterpret_cast<float4*>(b.base + (long long)ch * b.row_stride + n0);
-#pragma unroll
-                        for (int k = 0; k < 4; k++) stg_stream(p + k, make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]));
-                    }
-                } break;
-                case OP_MODMAP: {
-                    const float lo = op.p[0], span = sub(op.p[1], op.p[0]);
-#pragma unroll
-                    for (int i = 0; i < kChunk; i++) {
-                        float y = dv(add(acc[i], 1.0f), 2.0f);
-                        acc[i] = add(lo, mul(span, clamp01(y)));
-                    }
-                } break;
-                case OP_GAIN: {
-                    float P[kChunk];
-                    load_param(0, P);
-#pragma unroll
-                    for (int i = 0; i < kChunk; i++) acc[i] = mul(acc[i], P[i]);
-                } break;
-                case OP_DISTORT: {
-                    float P[kChunk];
-                    load_param(0, P);
-                    const int mode = op.mode;
-                    if (mode == Fuzz) {  // nodes/distort.rs:146-172, per 128-sample reference block
-                        const float mx = block128_max_abs(acc);
-                        float z[kChunk];
-#pragma unroll
-                        for (int i = 0; i < kChunk; i++) {
-                            float q = dv(clipf(mul(acc[i], P[i])), mx);
-                            z[i] = copysignf(sub(1.0f, expf(copysignf(q, -1.0f))), -1.0f);
-                        }
-                        const float mz = block128_max_abs(z);
-#pragma unroll
-                        for (int i = 0; i < kChunk; i++) z[i] = dv(clipf(mul(z[i], mx)), mz);
-                        const float my = block128_max_abs(z);
-#pragma unroll
-                        for (int i = 0; i < kChunk; i++) acc[i] = dv(mul(z[i], mx), my);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < kChunk; i++) acc[i] = shape(mode, acc[i], P[i]);
-                    }
-                } break;
-                case OP_OVERDRIVE: {
-                    float B[kChunk], D[kChunk], L[kChunk];
-                    load_param(0, B);
-                    load_param(1, D);
-                    load_param(2, L);
-                    const float FRAC_PI_4 = 0.785398163397448309615660845819875721f;
-                    const float FRAC_2_PI = 0.636619772367581343075535053490057448f;
-#pragma unroll
-                    for (int i = 0; i < kChunk; i++) {
-                        const float x = acc[i];
-                        if (!(L[i] < 0.001f)) {
-                            float c = atanf(mul(FRAC_PI_4, mul(x, B[i])));
-                            float d = mul(FRAC_2_PI, c);
-                            float mix = add(mul(D[i], d), mul(sub(1.0f, D[i]), x));
-                            acc[i] = mul(mix, L[i]);
-                        }
-                    }
-                } break;
-                case OP_CHEBY: {
-                    const float lp = op.p[0], ln = op.p[1], tp = op.p[2], tn = op.p[3];
-#pragma unroll
-                    for (int i = 0; i < kChunk; i++) {
-                        const float x = acc[i];
-                        if (x >= 0.0f) { if (!(lp < 0.001f)) acc[i] = dv(tanhf(mul(x, lp)), tp); }
-                        else { if (!(ln < 0.001f)) acc[i] = dv(tanhf(mul(x, ln)), tn); }
-                    }
-                } break;
-                case OP_MIX: {
-                    float R[kChunk];
-                    load_param(0, R);
-                    const float4* s = vregs + (op.vreg * 4) * kThreads + t;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        float4 q = s[k * kThreads];
-                        const float b[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            const int i = 4 * k + e;
-                            acc[i] = add(mul(b[e], R[i]), mul(acc[i], sub(1.0f, R[i])));
-                        }
-                    }
-                } break;
-                case OP_COMB: {
-                    const RingDesc& r = prog.rings[op.aux & 0xff];
-                    const float decay = op.p[0];
-                    const int pslot = op.aux >> 8;  // 0 = not staged
-                    float* rrow = r.base + (long long)ch * r.D;
-                    if ((r.D & 15) == 0 && (r.pos & 15) == 0) {
-                        const long long slot = (r.pos + n0) % r.D;
-                        float old[kChunk];
-                        if (pslot) {
-                            const float4* s = stage + ((parity * prog.n_prefetch + (pslot - 1)) * 4) * kThreads + t;
-#pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                float4 q = s[k * kThreads];
-                                old[4 * k] = q.x; old[4 * k + 1] = q.y; old[4 * k + 2] = q.z; old[4 * k + 3] = q.w;
-                            }
-                        } else if (active) {
-                            const float4* p = reinterpret_cast<const float4*>(rrow + slot);
-#pragma unroll
-                            for (int k = 0; k < 4; k++) {
-                                float4 q = ldg_stream(p + k);
-                                old[4 * k] = q.x; old[4 * k + 1] = q.y; old[4 * k + 2] = q.z; old[4 * k + 3] = q.w;
-                            }
-                        }
-                        if (active) {
-#pragma unroll
-                            for (int i = 0; i < kChunk; i++) acc[i] = add(acc[i], mul(old[i], decay));
-                            float4* p = reinterpret_cast<float4*>(rrow + slot);
-#pragma unroll
-                            for (int k = 0; k < 4; k++) stg_stream(p + k, make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]));
-                        }
-                    } else if (active) {  // ring length not a multiple of 16: element-wise wrap
-                        long long slot = (r.pos + n0) % r.D;
-#pragma unroll
-                        for (int i = 0; i < kChunk; i++) {
-                            float o = __ldcg(rrow + slot);
-                            acc[i] = add(acc[i], mul(o, decay));
-                            __stcg(rrow + slot, acc[i]);
-                            if (++slot == r.D) slot = 0;
-                        }
-                    }
-                } break;
-                case OP_BIQUAD: {
-                    DF1 f;
-                    f.b0 = op.p[0]; f.b1 = op.p[1]; f.b2 = op.p[2]; f.a1 = op.p[3]; f.a2 = op.p[4];
-                    run_recurrence<G>(f, acc, tile, sm_state + op.aux * G, g, j, ch_ok || true ? valid_f4 : 0);
-                } break;
-                case OP_LP1: {
-                    LP1 f; f.r = op.p[0]; f.omr = op.p[1];
-                    run_recurrence<G>(f, acc, tile, sm_state + op.aux * G, g, j, valid_f4);
-                } break;
-                case OP_HP1: {
-                    HP1 f; f.r = op.p[0]; f.omr = op.p[1];
-                    run_recurrence<G>(f, acc, tile, sm_state + op.aux * G, g, j, valid_f4);
-                } break;
-                case OP_ENVELOPE: {
-                    Env f; f.ga = op.p[0]; f.gr = op.p[1];
-                    run_recurrence<G>(f, acc, tile, sm_state + op.aux * G, g, j, valid_f4);
-                } break;
-                default: break;
+        if constexpr (Chain::n > 0) {
+            run_static<G, Chain, 0>(prog, c, acc);
+        } else {
+            for (int ip = 0; ip < prog.n_ops; ip++) {
+                const Op& op = prog.ops[ip];
+                exec_op<G>(op.code, op.mode, op.pre, op, c, acc);
             }
         }
     }
-    cp_async_wait<0>();
+    cp_async_wait_all();
     __syncthreads();
     for (int i = t; i < n_states * G; i += kThreads) {
-        int s = i / G, c = c_begin + blockIdx.x * G + (i % G);
-        if (c < c_end) reinterpret_cast<float4*>(prog.states[s])[c] = sm_state[s * G + (i % G)];
+        int s = i / G, cc = c_begin + blockIdx.x * G + (i % G);
+        if (cc < c_end) reinterpret_cast<float4*>(prog.states[s])[cc] = c.sm_state[s * G + (i % G)];
     }
+}
+
+template <class Chain>
+bool chain_matches(const Program& p) {
+    if (Chain::n == 0 || p.n_ops != Chain::n) return false;
+    for (int i = 0; i < Chain::n; i++) {
+        const int s = Chain::sig(i);
+        const Op& o = p.ops[i];
+        if (o.code != (s & 0xff) || o.pre != ((s >> 16) & 0xff) || o.pflags != 0) return false;
+        if (o.code == OP_DISTORT && o.mode != ((s >> 8) & 0xff)) return false;
+    }
+    return true;
+}
+
+template <int G, class Chain>
+int launch_gc(const Program& prog, int c_begin, int c_end, int64_t T, int n_states, cudaStream_t st) {
+    const int smem = fused_smem_bytes(prog, G);
+    static int configured = -1;
+    static int n_sm = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(fused_kernel<G, Chain>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem;
+    }
+    if (!n_sm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
+    }
+    const int n_cta = (c_end - c_begin + G - 1) / G;
+    fused_kernel<G, Chain><<<n_cta, kThreads, smem, st>>>(prog, c_begin, c_end, (long long)T, n_states, n_sm);
+    return (int)cudaGetLastError();
 }
 
 template <int G>
 int launch_g(const Program& prog, int c_begin, int c_end, int64_t T, int n_states, cudaStream_t st) {
-    const int smem = fused_smem_bytes(prog, G);
-    static int configured = -1;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(fused_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
+    static const bool no_static = getenv("DSPB_NO_STATIC") != nullptr;
+    if (!no_static) {
+        if (chain_matches<ChainGDBR>(prog)) return launch_gc<G, ChainGDBR>(prog, c_begin, c_end, T, n_states, st);
+        if (chain_matches<ChainGDR>(prog)) return launch_gc<G, ChainGDR>(prog, c_begin, c_end, T, n_states, st);
+        if (chain_matches<ChainBB>(prog)) return launch_gc<G, ChainBB>(prog, c_begin, c_end, T, n_states, st);
+        if (chain_matches<ChainLH>(prog)) return launch_gc<G, ChainLH>(prog, c_begin, c_end, T, n_states, st);
+        if (chain_matches<ChainCopy>(prog)) return launch_gc<G, ChainCopy>(prog, c_begin, c_end, T, n_states, st);
     }
-    const int n_cta = (c_end - c_begin + G - 1) / G;
-    fused_kernel<G><<<n_cta, kThreads, smem, st>>>(prog, c_begin, c_end, (long long)T, n_states);
-    return (int)cudaGetLastError();
+    return launch_gc<G, ChainDynamic>(prog, c_begin, c_end, T, n_states, st);
 }
 
 }  // namespace
+// Exhaustive device-side proof that div_const(a, {b, r}) == a / b (IEEE) for ALL 2^32 dividends a that
+// it does not flag: the engine enables the 3-instruction division for a divisor only after this passed.
+namespace {
+__global__ void div_verify_kernel(float b, float r, unsigned long long* mism) {
+    const unsigned long long base = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * 256ull;
+    unsigned long long m = 0;
+    for (int k = 0; k < 256; k++) {
+        const float a = __uint_as_float((unsigned)(base + k));
+        float mn = kDivHi, mx = 0.0f;
+        const float q = div_const(a, ConstDiv{b, r}, mn, mx);
+        const float ref = __fdiv_rn(a, b);
+        if (div_const_accept(mn, mx) && __float_as_uint(q) != __float_as_uint(ref) && !(q != q && ref != ref)) m++;
+    }
+    if (m) atomicAdd(mism, m);
+}
+}  // namespace
+
+int verify_const_div(float b, float r, unsigned long long* mismatches) {
+    unsigned long long* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, 8);
+    if (e != cudaSuccess) return (int)e;
+    cudaMemset(d, 0, 8);
+    div_verify_kernel<<<65536, 256>>>(b, r, d);
+    e = cudaMemcpy(mismatches, d, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    return (int)e;
+}
 
 int fused_smem_bytes(const Program& prog, int G) {
     const int S = kTile / G;
-    size_t b = (size_t)kMaxStates * G * 16;
+    size_t b = (size_t)kMaxStates * G * 16 + (size_t)kThreads * 8;
     if (prog.needs_tile) b += (size_t)G * (S + 4) * 4;
-    b += (size_t)2 * prog.n_prefetch * kTile * 4;
+    b += (size_t)prog.n_prefetch * kTile * 4;
     b += (size_t)prog.n_vregs * kTile * 4;
     return (int)b;
 }

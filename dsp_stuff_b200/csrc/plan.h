@@ -18,7 +18,7 @@ constexpr int kThreads = 256;       // threads per CTA
 constexpr int kChunk = 16;          // consecutive samples per thread
 constexpr int kTile = kThreads * kChunk;  // 4096 samples per CTA tile
 constexpr int kRefBlock = 128;      // node.rs:257 BUF_SIZE
-constexpr int kMaxOps = 56;
+constexpr int kMaxOps = 48;
 constexpr int kMaxBufs = 12;
 constexpr int kMaxRings = 6;
 constexpr int kMaxStates = 12;
@@ -26,6 +26,7 @@ constexpr int kMaxPrefetch = 2;
 
 enum OpCode : uint8_t {
     OP_END = 0,
+    OP_NOP,        // only the fan-in prologue (pre) runs
     OP_ZERO,       // acc = 0
     OP_LOADG,      // acc = 0.0f + G[buf]           (first link of a fan-in sum, node.rs:181-183)
     OP_ADDG,       // acc = acc + G[buf]
@@ -33,7 +34,7 @@ enum OpCode : uint8_t {
     OP_ADDV,       // acc = acc + V[vreg]
     OP_COPYV,      // acc = V[vreg]                 (plain reload, no +0)
     OP_COPYG,      // acc = G[buf]
-    OP_DIVC,       // acc = acc / p0                (collect_and_average divisor, node.rs:189-191)
+    OP_DIVC,       // (lowering only: folded into the next op's `pre`) acc = acc / p0, node.rs:189-191
     OP_SAVEV,      // V[vreg] = acc
     OP_STOREG,     // G[buf] = acc
     OP_MODMAP,     // acc = p0 + (p1-p0)*clamp((acc+1)/2,0,1)   (lib.rs:138-146)
@@ -44,7 +45,7 @@ enum OpCode : uint8_t {
     OP_ADD,        // acc = acc + V[vreg]           (nodes/add.rs: a + b, acc = a)
     OP_MIX,        // acc = V[vreg]*r + acc*(1-r), r = P0 (nodes/mix.rs:45; acc = a, vreg = b)
     OP_COMB,       // acc = acc + ring*p0 ; ring = acc      (nodes/reverb.rs:87-103), ring index `aux`
-    OP_BIQUAD,     // exact DF1, coefs p0..p4 = b0,b1,b2,a1,a2; state slot `aux`
+    OP_BIQUAD,     // exact DF1, coefs p0..p3 = b0,b1,b2,a1 and Op::a2; state slot `aux`
     OP_LP1,        // y = x*p1 + p0*z ; z = y  (p0 = ratio, p1 = 1-ratio), state slot `aux`
     OP_HP1,        // z = x*p1 + p0*z ; y = x - z
     OP_ENVELOPE,   // p0 attack gain, p1 release gain, state slot `aux`
@@ -61,8 +62,10 @@ struct Op {
     uint8_t pv[3];    // vregs of tile-valued parameters
     uint8_t buf;      // global buffer index for LOADG/ADDG/STOREG, prefetch slot + 1 in `aux`
     uint16_t aux;     // ring / state slot, or prefetch slot (0 = none, k+1 = slot k)
-    uint16_t pad;
-    float p[6];
+    uint8_t pad;      // bit 0: p[1] holds a verified reciprocal of p[0] (exact_math.cuh div_const)
+    uint8_t pre;      // fan-in prologue folded into this op: 1 = acc = 0.0 + acc; 2 = acc /= p[4]; 4 = p[5] = 1/p[4] usable
+    float p[6];       // p[4], p[5]: fan-in divisor and its reciprocal when pre & 2
+    float a2;         // biquad: a2 (p[0..3] = b0, b1, b2, a1)
 };
 
 struct BufDesc {       // a [C x n] f32 array in global memory
@@ -94,6 +97,8 @@ struct Program {
 // Runs `prog` for channels [c_begin, c_end) and samples [0, T) of this call.  G in {1,2,4,8,16,32}.
 int launch_fused(const Program& prog, int G, int c_begin, int c_end, int64_t T, void* stream);
 int fused_smem_bytes(const Program& prog, int G);
+// Enumerates all 2^32 dividends on the device; *mismatches == 0 proves div_const exact for divisor b.
+int verify_const_div(float b, float r, unsigned long long* mismatches);
 
 enum FirMode { FIR_FFT = 0, FIR_DIRECT = 1 };
 struct FirPlan {
@@ -108,7 +113,8 @@ struct FirPlan {
 // U: [C x (hist_pad + T)] input incl. history; Y: [C x T] output.  started = samples seen before this call.
 int launch_fir(const FirPlan& fp, const float* U, int64_t u_stride, float* Y, int64_t y_stride, int c_begin, int c_end,
                int64_t T, int64_t started, void* stream, int* n_launches);
-// Computes H from taps on the device (f64 transform, same digit order as the f32 kernel).
-int fir_prepare_spectrum(int log2F, const double* taps_rev_host, int n_taps, float2* H_dev, void* stream);
+// Computes H from the (device-resident, reversed, f64) taps with the kernel's own forward passes in f64.
+int fir_prepare_spectrum(int log2F, const double* taps_rev_dev, int n_taps, float2* H_dev, void* stream);
+int fir_fft_max_taps();
 
 }  // namespace dspb
