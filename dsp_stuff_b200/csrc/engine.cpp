@@ -181,6 +181,9 @@ struct dspb_engine {
     std::vector<cudaEvent_t> ev_pool;
     int64_t last_launches = 0;
     int force_G = 0;
+    bool prof_on = false;
+    struct ProfRec { int step; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
     bool plan_only = false;
 
     int find(int64_t id) const {
@@ -189,6 +192,7 @@ struct dspb_engine {
         return -1;
     }
     ~dspb_engine() {
+        for (auto& r : prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
         for (auto e : ev_pool) cudaEventDestroy(e);
         if (s_h2d) cudaStreamDestroy(s_h2d);
         if (s_cmp) cudaStreamDestroy(s_cmp);
@@ -524,9 +528,15 @@ void Lowerer::close_fused() {
                 break;
             }
         }
-    char hdr[160];
-    snprintf(hdr, sizeof hdr, "fused segment: G=%d channels x S=%d samples per CTA, %d ops, %d smem vregs, %d prefetch slots\n", G,
-             S, P.n_ops, P.n_vregs, P.n_prefetch);
+    int alg = 0;  // ALGORITHMIC bytes per channel-sample of this kernel: 4 per global f32 read/write, 8 per ring
+    for (int i = 0; i < P.n_ops; i++) {
+        const int c = P.ops[i].code;
+        if (c == OP_LOADG || c == OP_ADDG || c == OP_COPYG || c == OP_STOREG) alg += 4;
+        if (c == OP_COMB) alg += 8;
+    }
+    char hdr[200];
+    snprintf(hdr, sizeof hdr, "fused segment: G=%d channels x S=%d samples per CTA, %d ops, %d smem vregs, %d prefetch slots, alg_bytes=%d\n", G,
+             S, P.n_ops, P.n_vregs, P.n_prefetch, alg);
     cur.text = hdr;
     for (size_t i = 0; i < txt.size(); i++) cur.text += "    " + txt[i] + "\n";
     steps.push_back(cur);
@@ -634,10 +644,10 @@ int Lowerer::lower() {
                 fs.fir_node = ni;
                 char b[160];
                 if (e.cfg.fir_mode == FIR_FFT)
-                    snprintf(b, sizeof b, "fir step: %s, %zu taps, overlap-save FFT 2^%d, two channels per transform\n", tag.c_str(),
+                    snprintf(b, sizeof b, "fir step: %s, %zu taps, overlap-save FFT 2^%d, two channels per transform, alg_bytes=8\n", tag.c_str(),
                              nd.taps.size(), e.cfg.fir_fft_log2);
                 else
-                    snprintf(b, sizeof b, "fir step: %s, %zu taps, direct f64 sum in reference order\n", tag.c_str(), nd.taps.size());
+                    snprintf(b, sizeof b, "fir step: %s, %zu taps, direct f64 sum in reference order, alg_bytes=8\n", tag.c_str(), nd.taps.size());
                 fs.text = b;
                 steps.push_back(fs);
                 logical_step += 2;
@@ -868,7 +878,16 @@ int topo_sort(dspb_engine* e) {
 
 // Bind per-call pointers and launch every step for channels [c0, c1).
 int run_steps(dspb_engine* e, const float* const* d_in, float* const* d_out, int64_t n, int c0, int c1, cudaStream_t st) {
+    int step_idx = -1;
     for (auto& s : e->steps) {
+        step_idx++;
+        struct ProfScope {  // CUDA events around this step on the launching stream
+            dspb_engine* e; cudaStream_t st; bool on; cudaEvent_t a{}, b{}; int idx;
+            ProfScope(dspb_engine* e_, cudaStream_t st_, int idx_) : e(e_), st(st_), on(e_->prof_on && e_->prof.size() < 16384), idx(idx_) {
+                if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+            }
+            ~ProfScope() { if (on) { cudaEventRecord(b, st); e->prof.push_back({idx, a, b}); } }
+        } prof_scope(e, st, step_idx);
         if (s.kind == STEP_FUSED) {
             Program& P = s.prog;
             for (size_t b = 0; b < s.binds.size(); b++) {
@@ -1209,6 +1228,33 @@ int dspb_node_port_index(dspb_engine* e, int64_t node_id, const char* port, int 
     if (p < 0) return fail(DSPB_ERR_UNKNOWN_PORT, "node type '%s' has no %s port '%s'", nt.cfg_name, is_output ? "output" : "input", port);
     *out = p;
     return DSPB_OK;
+}
+
+int dspb_profile_enable(dspb_engine* e, int on) {
+    if (!e) return fail(DSPB_ERR_INVALID, "null engine");
+    e->prof_on = on != 0;
+    return DSPB_OK;
+}
+
+int dspb_profile_read(dspb_engine* e, double* ms_total, int64_t* rounds, int cap) {
+    if (!e) return fail(DSPB_ERR_INVALID, "null engine");
+    if (!e->plan_only) CUDA_TRY(cudaDeviceSynchronize());
+    for (int i = 0; i < cap; i++) {
+        if (ms_total) ms_total[i] = 0.0;
+        if (rounds) rounds[i] = 0;
+    }
+    for (auto& r : e->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        if (r.step < cap) {
+            if (ms_total) ms_total[r.step] += ms;
+            if (rounds) rounds[r.step] += 1;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    e->prof.clear();
+    return (int)e->steps.size();
 }
 
 int64_t dspb_describe_plan(dspb_engine* e, char* buf, int64_t cap) {

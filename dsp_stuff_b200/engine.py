@@ -50,7 +50,7 @@ ABI_SYMBOLS = [
     "dspb_engine_create", "dspb_engine_destroy", "dspb_last_error", "dspb_abi_version", "dspb_node_add",
     "dspb_node_set_f32", "dspb_node_set_enum", "dspb_node_set_taps", "dspb_node_set_impulse_response", "dspb_link",
     "dspb_load_graph_json", "dspb_compile", "dspb_process", "dspb_node_process", "dspb_reset_state",
-    "dspb_node_get_i64", "dspb_node_port_index", "dspb_describe_plan",
+    "dspb_node_get_i64", "dspb_node_port_index", "dspb_describe_plan", "dspb_profile_enable", "dspb_profile_read",
 ]
 
 _lib = None
@@ -83,6 +83,8 @@ def load_library(path: Optional[str] = None):
     L.dspb_reset_state.argtypes = [vp]
     L.dspb_node_get_i64.argtypes = [vp, i64, cp, ctypes.POINTER(i64)]
     L.dspb_node_port_index.argtypes = [vp, i64, cp, ctypes.c_int, ctypes.POINTER(ctypes.c_int32)]
+    L.dspb_profile_enable.argtypes = [vp, ctypes.c_int]
+    L.dspb_profile_read.argtypes = [vp, vp, vp, ctypes.c_int]
     L.dspb_describe_plan.argtypes = [vp, vp, i64]
     L.dspb_describe_plan.restype = i64
     if path is None:
@@ -176,6 +178,32 @@ class Engine:
         buf = ctypes.create_string_buffer(int(n))
         self._L.dspb_describe_plan(self._h, buf, n)
         return buf.value.decode()
+
+    def profile(self, on: bool = True):
+        self._ck(self._L.dspb_profile_enable(self._h, int(on)))
+
+    def profile_read(self):
+        """-> list of (total_ms, rounds) per schedule step, measured with CUDA events on the launch stream."""
+        cap = 64
+        ms = (ctypes.c_double * cap)()
+        rounds = (ctypes.c_int64 * cap)()
+        n = self._L.dspb_profile_read(self._h, ms, rounds, cap)
+        if n < 0:
+            self._ck(n)
+        return [(ms[i], rounds[i]) for i in range(min(n, cap))]
+
+    def plan_steps(self):
+        """Parses describe_plan(): per step its kind and ALGORITHMIC bytes per channel-sample
+        (4 B per global f32 read or write, 8 B per Reverb ring; SURVEY.md section 8d / DESIGN.md)."""
+        import re
+
+        steps = []
+        for line in self.describe_plan().splitlines():
+            if line.startswith("["):
+                m = re.search(r"alg_bytes=(\d+)", line)
+                steps.append({"kind": "fir" if "fir step" in line else "fused", "alg_bytes": int(m.group(1)) if m else 0,
+                              "text": line.split("] ", 1)[1]})
+        return steps
 
     @property
     def kernel_launches(self) -> int:

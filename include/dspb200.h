@@ -146,6 +146,13 @@ int dspb_reset_state(dspb_engine* e);
 int dspb_node_get_i64(dspb_engine* e, int64_t node_id, const char* key, int64_t* out);
 /* Port name -> local index, as PortStorage::get_idx on a freshly built node (node.rs:74-89). */
 int dspb_node_port_index(dspb_engine* e, int64_t node_id, const char* port, int is_output, int32_t* out);
+/* Per-step device timing (CUDA events on the launching stream around every step of the schedule).
+ * dspb_profile_enable(e, 1) starts recording on subsequent device-pointer dspb_process calls;
+ * dspb_profile_read synchronises, returns for each step i < cap the summed milliseconds and the
+ * number of launches-rounds measured, and clears the record.  Returns the number of steps. */
+int dspb_profile_enable(dspb_engine* e, int on);
+int dspb_profile_read(dspb_engine* e, double* ms_total, int64_t* rounds, int cap);
+
 /* Human-readable schedule (segments, ops, buffers) for DESIGN/profiling; returns bytes needed. */
 int64_t dspb_describe_plan(dspb_engine* e, char* buf, int64_t cap);
 
