@@ -156,6 +156,8 @@ struct Step {
     Program prog;   // STEP_FUSED
     int G = 1;
     int fir_node = -1;
+    int fir_out_term = -1;   // >= 0: the FIR kernel applies the sink's fan-in average and writes output terminal t directly
+    float fir_post_nf = 0.0f;
     // which prog.bufs entries are rebound per call: ext input terminal t (>=0), ext output terminal t, scratch, fir U/Y
     struct Bind { int kind; int idx; };  // kind 0 ext-in, 1 ext-out, 2 scratch, 3 fir U (idx=node), 4 fir Y (idx=node)
     std::vector<Bind> binds;             // parallel to prog.bufs
@@ -297,6 +299,7 @@ struct Lowerer {
     std::map<std::pair<int, int>, Value> values;  // (node, out port) -> value
     std::map<std::pair<int, int>, int> use_step;  // last step that uses the value
     std::vector<int> node_step;                   // step index in which a node's ops are emitted
+    std::set<int> fused_sinks;                    // output terminals written directly by a FIR step
     std::string err;
 
     explicit Lowerer(dspb_engine& en) : e(en) {}
@@ -627,6 +630,7 @@ int Lowerer::lower() {
                 values[{ni, 0}] = v;
             } break;
             case T_OUTPUT: {
+                if (fused_sinks.count(ni)) break;
                 int t = (int)(std::find(e.out_terms.begin(), e.out_terms.end(), ni) - e.out_terms.begin());
                 emit_avg(ni, 0);  // nodes/output.rs:223
                 Op o = mk(OP_STOREG);
@@ -642,13 +646,26 @@ int Lowerer::lower() {
                 Step fs;
                 fs.kind = STEP_FIR;
                 fs.fir_node = ni;
-                char b[160];
+                // A sink fed only by this node: fold its fan-in average into the FIR epilogue
+                if (e.out_links[ni][0].size() == 1) {
+                    const int dst = e.links[e.out_links[ni][0][0]].dst;
+                    if (e.nodes[dst]->type == T_OUTPUT && e.in_links[dst][0].size() == 1) {
+                        fs.fir_out_term = (int)(std::find(e.out_terms.begin(), e.out_terms.end(), dst) - e.out_terms.begin());
+                        fs.fir_post_nf = 0.0001f + 1.0f;
+                        fused_sinks.insert(dst);
+                    }
+                }
+                char b[200];
                 if (e.cfg.fir_mode == FIR_FFT)
                     snprintf(b, sizeof b, "fir step: %s, %zu taps, overlap-save FFT 2^%d, two channels per transform, alg_bytes=8\n", tag.c_str(),
                              nd.taps.size(), e.cfg.fir_fft_log2);
                 else
                     snprintf(b, sizeof b, "fir step: %s, %zu taps, direct f64 sum in reference order, alg_bytes=8\n", tag.c_str(), nd.taps.size());
                 fs.text = b;
+                if (fs.fir_out_term >= 0) {
+                    fs.text.pop_back();
+                    fs.text += ", epilogue (0.0 + y)/1.00010002 -> output terminal " + std::to_string(fs.fir_out_term) + "\n";
+                }
                 steps.push_back(fs);
                 logical_step += 2;
                 state_slot = 0;
@@ -927,9 +944,12 @@ int run_steps(dspb_engine* e, const float* const* d_in, float* const* d_out, int
             fp.H = reinterpret_cast<const float2*>(f.H.p);
             fp.taps = reinterpret_cast<const double*>(f.taps_dev.p);
             fp.divisor = f.enums[0] == 0 ? 1.0f / (float)f.taps.size() : 1.0f;  // fir.rs:187-190
+            fp.post_nf = s.fir_post_nf;
             const int64_t us = f.hist_pad + e->cfg.max_samples;
             int nl = 0;
-            int rc = launch_fir(fp, f.U[f.cur_u].p, us, f.Y.p, e->cfg.max_samples, c0, c1, n, f.started, st, &nl);
+            float* yp = s.fir_out_term >= 0 ? d_out[s.fir_out_term] : f.Y.p;
+            const int64_t ys = s.fir_out_term >= 0 ? n : e->cfg.max_samples;
+            int rc = launch_fir(fp, f.U[f.cur_u].p, us, yp, ys, c0, c1, n, f.started, st, &nl);
             if (rc) return fail(DSPB_ERR_CUDA, "fir kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
             e->last_launches += nl;
             // carry the last hist_pad samples into the other U buffer (front) for the next call

@@ -23,8 +23,8 @@ constexpr int kDirectTile = 256;
 // One thread per output sample; the CTA's input window lives in shared memory.
 __global__ void __launch_bounds__(kDirectTile)
 fir_direct_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, float* __restrict__ Y, long long y_stride,
-                  const double* __restrict__ taps, int N, long long T, long long started, float divisor, int c_begin,
-                  long long n_begin, long long n_end) {
+                  const double* __restrict__ taps, int N, long long T, long long started, float divisor, float post_nf,
+                  int c_begin, long long n_begin, long long n_end) {
     extern __shared__ float xw[];  // [kDirectTile + N - 1]
     const int ch = c_begin + blockIdx.y;
     const long long tile0 = n_begin + (long long)blockIdx.x * kDirectTile;
@@ -47,7 +47,9 @@ fir_direct_kernel(const float* __restrict__ U, long long u_stride, int hist_pad,
         const float* x = xw + (threadIdx.x + (N - 1) - (int)a);  // x_abs[0]
         for (int i = 0; i <= (int)a; i++) acc = __dadd_rn(acc, __dmul_rn((double)x[i], taps[i]));
     }
-    Y[(long long)ch * y_stride + n] = __fmul_rn((float)acc, divisor);
+    float y = __fmul_rn((float)acc, divisor);
+    if (post_nf != 0.0f) y = __fdiv_rn(__fadd_rn(0.0f, y), post_nf);  // fused sink fan-in average (node.rs:162-194)
+    Y[(long long)ch * y_stride + n] = y;
 }
 
 }  // namespace
@@ -68,7 +70,7 @@ int launch_fir_direct(const FirPlan& fp, const float* U, int64_t u_stride, float
     for (int c = 0; c < C; c += 65535) {  // gridDim.y limit
         dim3 grid((unsigned)tiles, (unsigned)std::min(65535, C - c));
         fir_direct_kernel<<<grid, kDirectTile, smem, st>>>(U, u_stride, fp.hist_pad, Y, y_stride, fp.taps, N, T, started,
-                                                          fp.divisor, c_begin + c, n_begin, n_end);
+                                                          fp.divisor, fp.post_nf, c_begin + c, n_begin, n_end);
     }
     return (int)cudaGetLastError();
 }

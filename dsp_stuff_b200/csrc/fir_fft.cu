@@ -31,11 +31,28 @@ constexpr int kNT = 256;       // threads
 constexpr int kPadded = kF + kF / 16;
 
 template <typename T>
-struct C2 {
+struct __align__(2 * sizeof(T)) C2 {
     T x, y;
 };
-template <typename T> __device__ __forceinline__ C2<T> operator+(C2<T> a, C2<T> b) { return {a.x + b.x, a.y + b.y}; }
-template <typename T> __device__ __forceinline__ C2<T> operator-(C2<T> a, C2<T> b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ C2<double> operator+(C2<double> a, C2<double> b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ C2<double> operator-(C2<double> a, C2<double> b) { return {a.x - b.x, a.y - b.y}; }
+// f32: one packed FADD2 per complex add/sub (sm_100 add/sub.f32x2), half the issue slots of two FADDs
+__device__ __forceinline__ unsigned long long pack2(C2<float> a) {
+    return (unsigned long long)__float_as_uint(a.x) | ((unsigned long long)__float_as_uint(a.y) << 32);
+}
+__device__ __forceinline__ C2<float> unpack2(unsigned long long r) {
+    return {__uint_as_float((unsigned)r), __uint_as_float((unsigned)(r >> 32))};
+}
+__device__ __forceinline__ C2<float> operator+(C2<float> a, C2<float> b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack2(a)), "l"(pack2(b)));
+    return unpack2(d);
+}
+__device__ __forceinline__ C2<float> operator-(C2<float> a, C2<float> b) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pack2(a)), "l"(pack2(b)));
+    return unpack2(d);
+}
 template <typename T> __device__ __forceinline__ C2<T> cmul(C2<T> a, C2<T> w) { return {a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x}; }
 template <typename T> __device__ __forceinline__ C2<T> cmulc(C2<T> a, C2<T> w) { return {a.x * w.x + a.y * w.y, a.y * w.x - a.x * w.y}; }  // a * conj(w)
 
@@ -114,89 +131,151 @@ __device__ __forceinline__ void ifft_dit(C2<T> (&v)[R]) {
 __host__ __device__ constexpr int bitrev3(int s) { return ((s & 1) << 2) | (s & 2) | ((s >> 2) & 1); }
 __device__ __forceinline__ int pad(int p) { return p + (p >> 4); }
 
-// twiddles w^q, q = 1..7, from three table look-ups (w, w^2, w^4) and four products
+// Twiddle source.  W[k] = exp(-2 pi i k / F) factorised as coarse[k >> 4] * fine[k & 15] (512 + 16
+// entries, 4.1 KB of shared memory instead of an L2-resident 64 KB table).
+constexpr int kCoarse = kF / 16, kFine = 16;
 template <typename T>
-__device__ __forceinline__ void twiddles8(const C2<T>* __restrict__ W, int k1, C2<T> (&w)[8]) {
-    w[1] = W[k1 & (kF - 1)];
-    w[2] = W[(2 * k1) & (kF - 1)];
-    w[4] = W[(4 * k1) & (kF - 1)];
+struct Tw {
+    const C2<T>* coarse;  // [512] exp(-2 pi i m / 512)
+    const C2<T>* fine;    // [16]  exp(-2 pi i b / 8192)
+    __device__ __forceinline__ C2<T> at(int k) const {
+        k &= kF - 1;
+        const C2<T> c = coarse[k >> 4];
+        if ((k & 15) == 0) return c;
+        return cmul(c, fine[k & 15]);
+    }
+};
+// twiddles w^q, q = 1..7, from three look-ups (w, w^2, w^4) and four products.  STEP = F/M: every index is
+// a multiple of STEP, so look-ups whose index is a multiple of 16 need no fine factor.
+template <int STEP, typename T>
+__device__ __forceinline__ void twiddles8(const Tw<T>& W, int k1, C2<T> (&w)[8]) {
+    if constexpr (STEP % 16 == 0) {
+        w[1] = W.coarse[(k1 >> 4) & (kCoarse - 1)];
+        w[2] = W.coarse[(k1 >> 3) & (kCoarse - 1)];
+        w[4] = W.coarse[(k1 >> 2) & (kCoarse - 1)];
+    } else if constexpr (STEP % 8 == 0) {
+        w[1] = W.at(k1);
+        w[2] = W.coarse[(k1 >> 3) & (kCoarse - 1)];
+        w[4] = W.coarse[(k1 >> 2) & (kCoarse - 1)];
+    } else {
+        w[1] = W.at(k1);
+        w[2] = W.at(2 * k1);
+        w[4] = W.at(4 * k1);
+    }
     w[3] = cmul(w[1], w[2]);
     w[5] = cmul(w[1], w[4]);
     w[6] = cmul(w[2], w[4]);
     w[7] = cmul(w[3], w[4]);
 }
+template <typename T, typename TG>
+__device__ __forceinline__ Tw<T> load_tables(C2<T>* sm, const TG* __restrict__ Wg, int t) {
+    // sm: [512 + 16]; Wg: the full F-entry table in global memory
+    for (int i = t; i < kCoarse; i += kNT) sm[i] = C2<T>{(T)Wg[16 * i].x, (T)Wg[16 * i].y};
+    if (t < kFine) sm[kCoarse + t] = C2<T>{(T)Wg[t].x, (T)Wg[t].y};
+    return Tw<T>{sm, sm + kCoarse};
+}
 
-// forward radix-8 pass on the shared array: sub-transform size M, L = M/8
+// forward radix-8 pass on the shared array: sub-transform size M, L = M/8.  Butterfly u = t + 256 k of
+// thread t has j = u % L; for L <= 256 that is the same for every k, so the twiddles are loop-invariant.
 template <int M, typename T>
-__device__ __forceinline__ void fwd_pass8(C2<T>* a, const C2<T>* __restrict__ W, int t) {
+__device__ __forceinline__ void fwd_pass8(C2<T>* a, const Tw<T>& W, int t) {
     constexpr int L = M / 8;
+    static_assert(L % 16 == 0, "constant padded stride needs L % 16 == 0");
+    constexpr int LP = L + L / 16;  // pad(base + r*L) == pad(base) + r*LP
+    constexpr bool kInvariant = (kNT % L) == 0;
+    C2<T> w[8];
+    if constexpr (kInvariant) twiddles8<kF / M>(W, (t % L) * (kF / M), w);
 #pragma unroll 1
     for (int k = 0; k < kF / 8 / kNT; k++) {
         const int u = t + kNT * k, b = u / L, j = u % L, base = b * M + j;
-        C2<T> v[8], w[8];
+        C2<T>* p = a + pad(base);
+        C2<T> v[8];
 #pragma unroll
-        for (int r = 0; r < 8; r++) v[r] = a[pad(base + r * L)];
-        twiddles8(W, j * (kF / M), w);
+        for (int r = 0; r < 8; r++) v[r] = p[r * LP];
+        if constexpr (!kInvariant) twiddles8<kF / M>(W, j * (kF / M), w);
         fft_dif<8>(v);
-        a[pad(base)] = v[0];
+        p[0] = v[0];
 #pragma unroll
-        for (int s = 1; s < 8; s++) a[pad(base + bitrev3(s) * L)] = cmul(v[s], w[bitrev3(s)]);
+        for (int s = 1; s < 8; s++) p[bitrev3(s) * LP] = cmul(v[s], w[bitrev3(s)]);
     }
 }
 template <int M, typename T>
-__device__ __forceinline__ void inv_pass8(C2<T>* a, const C2<T>* __restrict__ W, int t) {
+__device__ __forceinline__ void inv_pass8(C2<T>* a, const Tw<T>& W, int t) {
     constexpr int L = M / 8;
+    constexpr int LP = L + L / 16;
+    constexpr bool kInvariant = (kNT % L) == 0;
+    C2<T> w[8];
+    if constexpr (kInvariant) twiddles8<kF / M>(W, (t % L) * (kF / M), w);
 #pragma unroll 1
     for (int k = 0; k < kF / 8 / kNT; k++) {
         const int u = t + kNT * k, b = u / L, j = u % L, base = b * M + j;
-        C2<T> v[8], w[8];
-        twiddles8(W, j * (kF / M), w);
-        v[0] = a[pad(base)];
+        C2<T>* p = a + pad(base);
+        C2<T> v[8];
+        if constexpr (!kInvariant) twiddles8<kF / M>(W, j * (kF / M), w);
+        v[0] = p[0];
 #pragma unroll
-        for (int s = 1; s < 8; s++) v[s] = cmulc(a[pad(base + bitrev3(s) * L)], w[bitrev3(s)]);
+        for (int s = 1; s < 8; s++) v[s] = cmulc(p[bitrev3(s) * LP], w[bitrev3(s)]);
         ifft_dit<8>(v);
 #pragma unroll
-        for (int r = 0; r < 8; r++) a[pad(base + r * L)] = v[r];
+        for (int r = 0; r < 8; r++) p[r * LP] = v[r];
     }
 }
 
 // ---- the convolution kernel --------------------------------------------------------------------------
+// Ne = effective tap count: N padded with zero taps so that Ne - 1 is a multiple of 4.  Then every window
+// start (s0 - (Ne-1), s0 a multiple of V = F - Ne + 1) and every output run is 16-byte aligned and the
+// first / last pass move two consecutive samples per 64-bit access.
+// post: optional epilogue "acc = 0.0 + y; acc /= post_nf" = the fan-in average of a sink fed only by this
+// node (node.rs:162-194, nodes/output.rs:223), so no separate kernel has to touch the output again.
 __global__ void __launch_bounds__(kNT, 3)
 fir_fft_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, float* __restrict__ Y, long long y_stride,
-               const float2* __restrict__ Hg, const float2* __restrict__ Wg, int N, long long T, float divisor, int c_begin,
-               int c_end) {
+               const float2* __restrict__ Hg, const float2* __restrict__ Wg, int Ne, long long T, float divisor, float post_nf,
+               int c_begin, int c_end) {
     extern __shared__ float2 smem_f2[];
     C2<float>* a = reinterpret_cast<C2<float>*>(smem_f2);
-    const C2<float>* W = reinterpret_cast<const C2<float>*>(Wg);
-    const C2<float>* H = reinterpret_cast<const C2<float>*>(Hg);
     const int t = threadIdx.x;
-    const int V = kF - N + 1;  // valid outputs per segment
+    const Tw<float> W = load_tables<float>(a + kPadded, Wg, t);
+    const C2<float>* H = reinterpret_cast<const C2<float>*>(Hg);
+    const int V = kF - Ne + 1;  // valid outputs per segment (multiple of 4)
     const long long s0 = (long long)blockIdx.x * V;
-    const long long w0 = s0 - (N - 1);  // call-relative index of window sample 0 (>= -hist_pad)
+    const long long w0 = s0 - (Ne - 1);  // call-relative index of window sample 0 (>= -hist_pad), multiple of 4
     const int chA = c_begin + 2 * blockIdx.y, chB = chA + 1;
     const bool hasB = chB < c_end;
-    const float* rowA = U + (long long)chA * u_stride + hist_pad;
-    const float* rowB = U + (long long)(hasB ? chB : chA) * u_stride + hist_pad;
+    const float* rowA = U + (long long)chA * u_stride + hist_pad + w0;
+    const float* rowB = U + (long long)(hasB ? chB : chA) * u_stride + hist_pad + w0;
+    const long long lim = T - w0;  // window samples >= lim lie beyond this call's input: zeros
+    __syncthreads();               // twiddle tables visible
 
-    // forward pass 1 (M = F, radix 8): operands straight from global memory
+    // forward pass 1 (M = F, radix 8): operands straight from global memory, two butterflies per step
     {
         constexpr int L = kF / 8;
 #pragma unroll 1
-        for (int k = 0; k < kF / 8 / kNT; k++) {
-            const int j = t + kNT * k;
-            C2<float> v[8], w[8];
+        for (int k = 0; k < kF / 8 / kNT / 2; k++) {
+            const int j = 2 * (t + kNT * k);
+            C2<float> v0[8], v1[8], w[8];
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-                const long long n = w0 + j + r * L;
-                const bool in = n < T;
-                v[r].x = in ? __ldg(rowA + n) : 0.0f;
-                v[r].y = (in && hasB) ? __ldg(rowB + n) : 0.0f;
+                const int n = j + r * L;
+                float2 xa = make_float2(0.f, 0.f), xb = make_float2(0.f, 0.f);
+                if (n < lim) {  // T, w0 and n are even: the pair is inside or outside together
+                    xa = __ldg(reinterpret_cast<const float2*>(rowA + n));
+                    if (hasB) xb = __ldg(reinterpret_cast<const float2*>(rowB + n));
+                }
+                v0[r] = C2<float>{xa.x, xb.x};
+                v1[r] = C2<float>{xa.y, xb.y};
             }
-            twiddles8(W, j, w);
-            fft_dif<8>(v);
-            a[pad(j)] = v[0];
+            constexpr int LP = L + L / 16;
+            C2<float>* p = a + pad(j);  // j is even: j and j + 1 share the padding offset
+            twiddles8<1>(W, j, w);
+            fft_dif<8>(v0);
+            p[0] = v0[0];
 #pragma unroll
-            for (int s = 1; s < 8; s++) a[pad(j + bitrev3(s) * L)] = cmul(v[s], w[bitrev3(s)]);
+            for (int s = 1; s < 8; s++) p[bitrev3(s) * LP] = cmul(v0[s], w[bitrev3(s)]);
+            twiddles8<1>(W, j + 1, w);
+            fft_dif<8>(v1);
+            p[1] = v1[0];
+#pragma unroll
+            for (int s = 1; s < 8; s++) p[1 + bitrev3(s) * LP] = cmul(v1[s], w[bitrev3(s)]);
         }
     }
     __syncthreads();
@@ -209,15 +288,17 @@ fir_fft_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, fl
     for (int k = 0; k < kF / 16 / kNT; k++) {
         const int u = t + kNT * k, base = 16 * u;
         C2<float> v[16];
+        float4 h[8];
+        const float4* h4 = reinterpret_cast<const float4*>(H + base);
+#pragma unroll
+        for (int s = 0; s < 8; s++) h[s] = __ldg(h4 + s);
 #pragma unroll
         for (int s = 0; s < 16; s++) v[s] = a[pad(base) + s];
         fft_dif<16>(v);
-        const float4* h4 = reinterpret_cast<const float4*>(H + base);
 #pragma unroll
         for (int s = 0; s < 16; s += 2) {
-            const float4 h = __ldg(h4 + s / 2);
-            v[s] = cmul(v[s], C2<float>{h.x, h.y});
-            v[s + 1] = cmul(v[s + 1], C2<float>{h.z, h.w});
+            v[s] = cmul(v[s], C2<float>{h[s / 2].x, h[s / 2].y});
+            v[s + 1] = cmul(v[s + 1], C2<float>{h[s / 2].z, h[s / 2].w});
         }
         ifft_dit<16>(v);
 #pragma unroll
@@ -228,27 +309,40 @@ fir_fft_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, fl
     __syncthreads();
     inv_pass8<kF / 8>(a, W, t);
     __syncthreads();
-    // inverse pass 1: results straight to global memory (only the V valid samples)
+    // inverse pass 1: results straight to global memory (only the V valid samples), two samples per store
     {
         constexpr int L = kF / 8;
-        float* outA = Y + (long long)chA * y_stride;
-        float* outB = Y + (long long)chB * y_stride;
+        float* outA = Y + (long long)chA * y_stride + s0 - (Ne - 1);
+        float* outB = Y + (long long)chB * y_stride + s0 - (Ne - 1);
+        const bool post = post_nf != 0.0f;
 #pragma unroll 1
-        for (int k = 0; k < kF / 8 / kNT; k++) {
-            const int j = t + kNT * k;
-            C2<float> v[8], w[8];
-            twiddles8(W, j, w);
-            v[0] = a[pad(j)];
+        for (int k = 0; k < kF / 8 / kNT / 2; k++) {
+            const int j = 2 * (t + kNT * k);
+            C2<float> v0[8], v1[8], w[8];
+            constexpr int LP = L + L / 16;
+            const C2<float>* p = a + pad(j);
+            twiddles8<1>(W, j, w);
+            v0[0] = p[0];
 #pragma unroll
-            for (int s = 1; s < 8; s++) v[s] = cmulc(a[pad(j + bitrev3(s) * L)], w[bitrev3(s)]);
-            ifft_dit<8>(v);
+            for (int s = 1; s < 8; s++) v0[s] = cmulc(p[bitrev3(s) * LP], w[bitrev3(s)]);
+            ifft_dit<8>(v0);
+            twiddles8<1>(W, j + 1, w);
+            v1[0] = p[1];
+#pragma unroll
+            for (int s = 1; s < 8; s++) v1[s] = cmulc(p[1 + bitrev3(s) * LP], w[bitrev3(s)]);
+            ifft_dit<8>(v1);
 #pragma unroll
             for (int r = 0; r < 8; r++) {
                 const int n = j + r * L;
-                const long long o = s0 + n - (N - 1);
-                if (n >= N - 1 && o < T) {
-                    outA[o] = __fmul_rn(v[r].x, divisor);
-                    if (hasB) outB[o] = __fmul_rn(v[r].y, divisor);
+                if (n >= Ne - 1 && n < lim) {
+                    float2 ya = make_float2(__fmul_rn(v0[r].x, divisor), __fmul_rn(v1[r].x, divisor));
+                    float2 yb = make_float2(__fmul_rn(v0[r].y, divisor), __fmul_rn(v1[r].y, divisor));
+                    if (post) {
+                        ya.x = __fdiv_rn(__fadd_rn(0.0f, ya.x), post_nf); ya.y = __fdiv_rn(__fadd_rn(0.0f, ya.y), post_nf);
+                        yb.x = __fdiv_rn(__fadd_rn(0.0f, yb.x), post_nf); yb.y = __fdiv_rn(__fadd_rn(0.0f, yb.y), post_nf);
+                    }
+                    *reinterpret_cast<float2*>(outA + n) = ya;
+                    if (hasB) *reinterpret_cast<float2*>(outB + n) = yb;
                 }
             }
         }
@@ -260,8 +354,8 @@ __global__ void __launch_bounds__(kNT, 1)
 fir_spectrum_kernel(const double* __restrict__ taps_rev, int N, const double2* __restrict__ Wd, float2* __restrict__ Hout) {
     extern __shared__ double2 smem_d2[];
     C2<double>* a = reinterpret_cast<C2<double>*>(smem_d2);
-    const C2<double>* W = reinterpret_cast<const C2<double>*>(Wd);
     const int t = threadIdx.x;
+    const Tw<double> W = load_tables<double>(a + kPadded, Wd, t);
     for (int n = t; n < kF; n += kNT) a[pad(n)] = C2<double>{n < N ? taps_rev[N - 1 - n] : 0.0, 0.0};  // h[n] = taps[N-1-n]
     __syncthreads();
     fwd_pass8<kF>(a, W, t);
@@ -311,6 +405,7 @@ int ensure_tables() {
 }  // namespace
 
 int fir_fft_max_taps() { return kF / 2 + 1; }
+static int effective_taps(int n) { return (n - 1 + 3) / 4 * 4 + 1; }  // Ne - 1 multiple of 4
 
 int launch_fir_fft(const FirPlan& fp, const float* U, int64_t u_stride, float* Y, int64_t y_stride, int c_begin, int c_end,
                    int64_t T, int64_t started, cudaStream_t st, int* n_launches) {
@@ -319,18 +414,19 @@ int launch_fir_fft(const FirPlan& fp, const float* U, int64_t u_stride, float* Y
     int rc = ensure_tables();
     if (rc) return rc;
     static bool configured = false;
-    const int smem = kPadded * (int)sizeof(float2);
+    const int smem = (kPadded + kCoarse + kFine) * (int)sizeof(float2);
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(fir_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         configured = true;
     }
-    const int V = kF - fp.n_taps + 1;
+    const int Ne = effective_taps(fp.n_taps);
+    const int V = kF - Ne + 1;
     const long long n_seg = (T + V - 1) / V;
     const int pairs = (c_end - c_begin + 1) / 2;
     for (int p0 = 0; p0 < pairs; p0 += 65535) {
         dim3 grid((unsigned)n_seg, (unsigned)std::min(65535, pairs - p0));
-        fir_fft_kernel<<<grid, kNT, smem, st>>>(U, u_stride, fp.hist_pad, Y, y_stride, fp.H, g_tab.Wf, fp.n_taps, T, fp.divisor,
+        fir_fft_kernel<<<grid, kNT, smem, st>>>(U, u_stride, fp.hist_pad, Y, y_stride, fp.H, g_tab.Wf, Ne, T, fp.divisor, fp.post_nf,
                                                c_begin + 2 * p0, c_end);
         if (n_launches) *n_launches += 1;
     }
@@ -341,7 +437,7 @@ int fir_prepare_spectrum(int log2F, const double* taps_rev_dev, int n_taps, floa
     if (log2F != kLog2F || n_taps > fir_fft_max_taps()) return (int)cudaErrorInvalidValue;
     int rc = ensure_tables();
     if (rc) return rc;
-    const int smem = kPadded * (int)sizeof(double2);
+    const int smem = (kPadded + kCoarse + kFine) * (int)sizeof(double2);
     cudaError_t e = cudaFuncSetAttribute(fir_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     fir_spectrum_kernel<<<1, kNT, smem, (cudaStream_t)stream>>>(taps_rev_dev, n_taps, g_tab.Wd, H_dev);

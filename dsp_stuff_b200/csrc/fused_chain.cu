@@ -548,10 +548,11 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
 
 // Compile-time op signatures of the BASELINE chains: same exec_op code, opcodes constant-folded.
 // sig(i) packs code | mode << 8 | pre << 16; n = 0 selects the run-time interpreter.
-struct ChainDynamic { static constexpr int n = 0; __host__ __device__ static constexpr int sig(int) { return 0; } };
+struct ChainDynamic { static constexpr int n = 0; static constexpr int rec = 0; __host__ __device__ static constexpr int sig(int) { return 0; } };
 #define DSPB_SIG(code, mode, pre) ((code) | ((mode) << 8) | ((pre) << 16))
 struct ChainGDBR {  // src -> gain -> distort(SoftClip) -> biquad -> reverb -> store   (config 3 / target front end)
     static constexpr int n = 6;
+    static constexpr int rec = 3;
     __host__ __device__ static constexpr int sig(int i) {
         return i == 0 ? DSPB_SIG(OP_LOADG, 0, 0) : i == 1 ? DSPB_SIG(OP_GAIN, 0, 6) : i == 2 ? DSPB_SIG(OP_DISTORT, SoftClip, 7)
              : i == 3 ? DSPB_SIG(OP_BIQUAD, 0, 7) : i == 4 ? DSPB_SIG(OP_COMB, 0, 7) : DSPB_SIG(OP_STOREG, 0, 7);
@@ -559,6 +560,7 @@ struct ChainGDBR {  // src -> gain -> distort(SoftClip) -> biquad -> reverb -> s
 };
 struct ChainGDR {  // src -> gain -> distort(SoftClip) -> reverb -> store   (config 1)
     static constexpr int n = 5;
+    static constexpr int rec = -1;
     __host__ __device__ static constexpr int sig(int i) {
         return i == 0 ? DSPB_SIG(OP_LOADG, 0, 0) : i == 1 ? DSPB_SIG(OP_GAIN, 0, 6) : i == 2 ? DSPB_SIG(OP_DISTORT, SoftClip, 7)
              : i == 3 ? DSPB_SIG(OP_COMB, 0, 7) : DSPB_SIG(OP_STOREG, 0, 7);
@@ -566,18 +568,21 @@ struct ChainGDR {  // src -> gain -> distort(SoftClip) -> reverb -> store   (con
 };
 struct ChainBB {  // src -> biquad -> biquad -> store   (config 2)
     static constexpr int n = 4;
+    static constexpr int rec = -1;
     __host__ __device__ static constexpr int sig(int i) {
         return i == 0 ? DSPB_SIG(OP_LOADG, 0, 0) : i == 1 ? DSPB_SIG(OP_BIQUAD, 0, 6) : i == 2 ? DSPB_SIG(OP_BIQUAD, 0, 7) : DSPB_SIG(OP_STOREG, 0, 7);
     }
 };
 struct ChainLH {  // src -> low_pass -> high_pass -> store   (config 2, one-pole variant)
     static constexpr int n = 4;
+    static constexpr int rec = -1;
     __host__ __device__ static constexpr int sig(int i) {
         return i == 0 ? DSPB_SIG(OP_LOADG, 0, 0) : i == 1 ? DSPB_SIG(OP_LP1, 0, 6) : i == 2 ? DSPB_SIG(OP_HP1, 0, 7) : DSPB_SIG(OP_STOREG, 0, 7);
     }
 };
 struct ChainCopy {  // G -> (/nf) -> store   (the segment after a Fir node)
     static constexpr int n = 2;
+    static constexpr int rec = -1;
     __host__ __device__ static constexpr int sig(int i) { return i == 0 ? DSPB_SIG(OP_LOADG, 0, 0) : DSPB_SIG(OP_STOREG, 0, 6); }
 };
 
@@ -659,6 +664,268 @@ fused_kernel(const __grid_constant__ Program prog, int c_begin, int c_end, long 
     }
 }
 
+
+// ======================= warp-specialised variant: one recurrence, fully overlapped =======================
+// For programs with exactly one recurrence op (biquad / low_pass / envelope) and no shared-memory vregs.
+// 9 warps: warps 0-7 ("E") run the time-parallel ops, warp 8 ("R") runs nothing but the lane = channel
+// feedback loop.  Tiles are double-buffered: in iteration i the E warps run the ops before the recurrence
+// for tile i (and hand tile buffer i&1 to R), then the ops after it for tile i-1 (once R is done with it),
+// so the sequential 12-cycle-per-sample chain is hidden behind elementwise work of neighbouring tiles.
+// Hand-offs use named barriers (bar.arrive / bar.sync with the 288-thread count).
+constexpr int kWsThreads = kThreads + 32;
+enum { BAR_FULL0 = 1, BAR_FULL1 = 2, BAR_DONE0 = 3, BAR_DONE1 = 4, BAR_EONLY = 5 };
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <int G, class Core>
+__device__ __forceinline__ void ws_recurrence_warp(Core core, float* tiles, const float4* st_in, float4* st_out, int lane,
+                                                   bool ch_ok, long long n_tiles, long long T) {
+    using Q = Geo<G>;
+    float4 s = make_float4(0, 0, 0, 0);
+    if (lane < G && ch_ok) s = *st_in;
+    core.load(s);
+    for (long long i = 0; i < n_tiles; i++) {
+        const int b = (int)(i & 1);
+        const long long rem = T - i * Q::S;
+        const int valid_f4 = (int)((rem < Q::S ? rem : Q::S) / 4);
+        bar_sync(BAR_FULL0 + b, kWsThreads);
+        if (lane < G) {
+            float4* r = reinterpret_cast<float4*>(tiles + b * (G * Q::ROW) + lane * Q::ROW);
+            float4 x = r[swz(0)];
+            for (int m = 0; m < valid_f4; m++) {
+                float4 nx = x;
+                if (m + 1 < valid_f4) nx = r[swz(m + 1)];
+                x.x = core.step(x.x);
+                x.y = core.step(x.y);
+                x.z = core.step(x.z);
+                x.w = core.step(x.w);
+                r[swz(m)] = x;
+                x = nx;
+            }
+        }
+        __threadfence_block();  // bar.arrive alone orders nothing: make the tile visible first
+        __syncwarp();
+        bar_arrive(BAR_DONE0 + b, kWsThreads);
+    }
+    if (lane < G && ch_ok) {
+        core.save(s);
+        *st_out = s;
+    }
+}
+
+template <int G, class Chain, int I, int END>
+__device__ __forceinline__ void run_static_range(const Program& prog, const Ctx<G>& c, float (&acc)[kChunk]) {
+    if constexpr (I < END) {
+        constexpr int s = Chain::sig(I);
+        exec_op<G>(s & 0xff, (s >> 8) & 0xff, (s >> 16) & 0xff, prog.ops[I], c, acc);
+        run_static_range<G, Chain, I + 1, END>(prog, c, acc);
+    }
+}
+
+template <int G, class Chain>
+__global__ void __launch_bounds__(kWsThreads, 3)
+fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, long long T, int n_sm, int rec_index) {
+    using Q = Geo<G>;
+    extern __shared__ float4 smem4[];
+    const int t = threadIdx.x;
+    // shared memory: [G] x-state (float2) | edge[256] | tiles[2][G*ROW] | stage
+    float2* xstate = reinterpret_cast<float2*>(smem4);
+    float2* edge = xstate + 32;
+    float* tiles = reinterpret_cast<float*>(edge + kThreads);
+    float4* stage = reinterpret_cast<float4*>(tiles + 2 * G * Q::ROW);
+    const long long n_tiles = (T + Q::S - 1) / Q::S;
+    const Op& rop = prog.ops[rec_index];
+    const int rcode = Chain::n > 0 ? (Chain::sig(Chain::rec) & 0xff) : rop.code;
+    float* stp = prog.states[rop.aux];
+    (void)n_sm;
+
+    if (t >= kThreads) {  // ---------------- R warp ----------------
+        const int lane = t - kThreads;
+        const int ch = c_begin + blockIdx.x * G + lane;
+        const bool ok = lane < G && ch < c_end;
+        const float4* sin = reinterpret_cast<const float4*>(stp) + (ok ? ch : 0);
+        float4* sout = reinterpret_cast<float4*>(stp) + (ok ? ch : 0);
+        if (rcode == OP_BIQUAD) {
+            DF1Core core; core.a1 = rop.p[3]; core.a2 = rop.a2;
+            // y1, y2 live in .z/.w; the E warps own .x/.y (x1, x2) and write them separately at the end
+            float4 s = make_float4(0, 0, 0, 0);
+            if (ok) s = *sin;
+            core.load(s);
+            using QQ = Geo<G>;
+            for (long long i = 0; i < n_tiles; i++) {
+                const int b = (int)(i & 1);
+                const long long rem = T - i * QQ::S;
+                const int valid_f4 = (int)((rem < QQ::S ? rem : QQ::S) / 4);
+                bar_sync(BAR_FULL0 + b, kWsThreads);
+                if (lane < G) {
+                    float4* r = reinterpret_cast<float4*>(tiles + b * (G * QQ::ROW) + lane * QQ::ROW);
+                    float4 x = r[swz(0)];
+                    for (int m = 0; m < valid_f4; m++) {
+                        float4 nx = x;
+                        if (m + 1 < valid_f4) nx = r[swz(m + 1)];
+                        x.x = core.step(x.x); x.y = core.step(x.y); x.z = core.step(x.z); x.w = core.step(x.w);
+                        r[swz(m)] = x;
+                        x = nx;
+                    }
+                }
+                __threadfence_block();
+                __syncwarp();
+                bar_arrive(BAR_DONE0 + b, kWsThreads);
+            }
+            if (ok) { float* f = reinterpret_cast<float*>(sout); f[2] = core.y1; f[3] = core.y2; }
+        } else if (rcode == OP_LP1) {
+            OnePoleCore core; core.r = rop.p[0];
+            ws_recurrence_warp<G>(core, tiles, sin, sout, lane, ok, n_tiles, T);
+        } else {
+            EnvCore core; core.ga = rop.p[0]; core.gr = rop.p[1];
+            ws_recurrence_warp<G>(core, tiles, sin, sout, lane, ok, n_tiles, T);
+        }
+        return;
+    }
+
+    // ---------------- E warps ----------------
+    Ctx<G> c;
+    c.prog = &prog;
+    c.t = t;
+    c.g = t / Q::TPC;
+    c.j = t % Q::TPC;
+    c.ch = c_begin + blockIdx.x * G + c.g;
+    c.ch_ok = c.ch < c_end;
+    c.T = T;
+    c.sm_state = nullptr;
+    c.edge = edge;
+    c.stage = stage;
+    c.vregs = nullptr;
+    c.n_tiles = n_tiles;
+    c.tc.tile = tiles;
+    c.tc.g = c.g;
+    c.tc.j = c.j;
+    c.tc.rec_warp = 8;
+    if (t < G) {
+        const int ch = c_begin + blockIdx.x * G + t;
+        xstate[t] = (rcode == OP_BIQUAD && ch < c_end) ? *reinterpret_cast<const float2*>(stp + 4 * (long long)ch) : make_float2(0.f, 0.f);
+    }
+    for (int s = 0; s < prog.n_prefetch; s++) c.issue_prefetch(s, 0);
+    bar_sync(BAR_EONLY, kThreads);
+
+    auto set_tile = [&](long long ti) {
+        c.tile_i = ti;
+        c.n0 = ti * Q::S + (long long)c.j * kChunk;
+        c.active = c.ch_ok && c.n0 < T;
+        const long long rem = T - ti * Q::S;
+        c.tc.valid_f4 = (int)((rem < Q::S ? rem : Q::S) / 4);
+        c.j_last = c.tc.valid_f4 / 4 - 1;
+    };
+
+    for (long long i = 0; i <= n_tiles; i++) {
+        bar_sync(BAR_EONLY, kThreads);  // ring hazards across tiles, edge[] reuse
+        cp_async_wait_all();
+        float acc[kChunk];
+        if (i < n_tiles) {  // ---- ops before the recurrence, tile i ----
+            set_tile(i);
+#pragma unroll
+            for (int k = 0; k < kChunk; k++) acc[k] = 0.0f;
+            if constexpr (Chain::n > 0) run_static_range<G, Chain, 0, Chain::rec>(prog, c, acc);
+            else
+                for (int ip = 0; ip < rec_index; ip++) exec_op<G>(prog.ops[ip].code, prog.ops[ip].mode, prog.ops[ip].pre, prog.ops[ip], c, acc);
+            // the recurrence op's own prologue and feed-forward part
+            const int rpre = Chain::n > 0 ? ((Chain::sig(Chain::rec) >> 16) & 0xff) : rop.pre;
+            if (rpre & 1) {
+#pragma unroll
+                for (int k = 0; k < kChunk; k++) acc[k] = add(0.0f, acc[k]);
+            }
+            if (rpre & 2) div16(acc, ConstDiv{rop.p[4], rop.p[5]}, rpre & 4);
+            if (rcode == OP_BIQUAD) {
+                const float b0 = rop.p[0], b1 = rop.p[1], b2 = rop.p[2];
+                edge[t] = make_float2(acc[14], acc[15]);
+                bar_sync(BAR_EONLY, kThreads);
+                float xm1, xm2;
+                if (c.j == 0) { const float2 s2 = xstate[c.g]; xm1 = s2.x; xm2 = s2.y; }
+                else { const float2 e = edge[t - 1]; xm2 = e.x; xm1 = e.y; }
+                const float nx1 = acc[15], nx2 = acc[14];
+                float pm1 = acc[0], pm2;
+                acc[0] = add(add(mul(b0, acc[0]), mul(b1, xm1)), mul(b2, xm2));
+                pm2 = pm1; pm1 = acc[1];
+                acc[1] = add(add(mul(b0, acc[1]), mul(b1, pm2)), mul(b2, xm1));
+#pragma unroll
+                for (int k = 2; k < kChunk; k++) {
+                    const float xi = acc[k];
+                    acc[k] = add(add(mul(b0, xi), mul(b1, pm1)), mul(b2, pm2));
+                    pm2 = pm1; pm1 = xi;
+                }
+                bar_sync(BAR_EONLY, kThreads);  // every thread has read xstate before it is replaced
+                if (c.j == c.j_last) xstate[c.g] = make_float2(nx1, nx2);
+            } else if (rcode == OP_LP1) {
+                const float omr = rop.p[1];
+#pragma unroll
+                for (int k = 0; k < kChunk; k++) acc[k] = mul(acc[k], omr);
+            } else {
+#pragma unroll
+                for (int k = 0; k < kChunk; k++) acc[k] = fabsf(acc[k]);
+            }
+            float4* row = reinterpret_cast<float4*>(tiles + (int)(i & 1) * (G * Q::ROW) + c.g * Q::ROW);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                row[4 * c.j + (k ^ ((c.j >> 1) & 3))] = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+            __threadfence_block();
+            bar_arrive(BAR_FULL0 + (int)(i & 1), kWsThreads);
+        }
+        if (i >= 1) {  // ---- ops after the recurrence, tile i-1 ----
+            const int b = (int)((i - 1) & 1);
+            bar_sync(BAR_DONE0 + b, kWsThreads);
+            set_tile(i - 1);
+            const float4* row = reinterpret_cast<const float4*>(tiles + b * (G * Q::ROW) + c.g * Q::ROW);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const float4 q = row[4 * c.j + (k ^ ((c.j >> 1) & 3))];
+                acc[4 * k] = q.x; acc[4 * k + 1] = q.y; acc[4 * k + 2] = q.z; acc[4 * k + 3] = q.w;
+            }
+            if constexpr (Chain::n > 0) run_static_range<G, Chain, Chain::rec + 1, Chain::n>(prog, c, acc);
+            else
+                for (int ip = rec_index + 1; ip < prog.n_ops; ip++) exec_op<G>(prog.ops[ip].code, prog.ops[ip].mode, prog.ops[ip].pre, prog.ops[ip], c, acc);
+        }
+    }
+    cp_async_wait_all();
+    bar_sync(BAR_EONLY, kThreads);
+    if (rcode == OP_BIQUAD && t < G) {
+        const int ch = c_begin + blockIdx.x * G + t;
+        if (ch < c_end) *reinterpret_cast<float2*>(stp + 4 * (long long)ch) = xstate[t];
+    }
+}
+
+int ws_smem_bytes(const Program& prog, int G) {
+    const int S = kTile / G;
+    return 32 * 8 + kThreads * 8 + 2 * G * (S + 4) * 4 + prog.n_prefetch * kTile * 4;
+}
+// index of the single recurrence op if the program qualifies for the warp-specialised kernel, else -1
+int ws_rec_index(const Program& p) {
+    if (p.n_vregs != 0) return -1;
+    int idx = -1;
+    for (int i = 0; i < p.n_ops; i++) {
+        const int c = p.ops[i].code;
+        if (c == OP_BIQUAD || c == OP_LP1 || c == OP_ENVELOPE) {
+            if (idx >= 0) return -1;
+            idx = i;
+        }
+        if (c == OP_HP1) return -1;
+    }
+    return idx;
+}
+
+template <int G, class Chain>
+int launch_ws(const Program& prog, int c_begin, int c_end, int64_t T, int rec_index, cudaStream_t st) {
+    const int smem = ws_smem_bytes(prog, G);
+    static int configured = -1;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(fused_kernel_ws<G, Chain>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = smem;
+    }
+    const int n_cta = (c_end - c_begin + G - 1) / G;
+    fused_kernel_ws<G, Chain><<<n_cta, kWsThreads, smem, st>>>(prog, c_begin, c_end, (long long)T, 148, rec_index);
+    return (int)cudaGetLastError();
+}
+
 template <class Chain>
 bool chain_matches(const Program& p) {
     if (Chain::n == 0 || p.n_ops != Chain::n) return false;
@@ -695,6 +962,12 @@ int launch_gc(const Program& prog, int c_begin, int c_end, int64_t T, int n_stat
 template <int G>
 int launch_g(const Program& prog, int c_begin, int c_end, int64_t T, int n_states, cudaStream_t st) {
     static const bool no_static = getenv("DSPB_NO_STATIC") != nullptr;
+    static const bool no_ws = getenv("DSPB_NO_WS") != nullptr;
+    const int rec = (G <= 32 && !no_ws) ? ws_rec_index(prog) : -1;
+    if (rec >= 0 && ws_smem_bytes(prog, G) <= 200 * 1024) {
+        if (!no_static && chain_matches<ChainGDBR>(prog)) return launch_ws<G, ChainGDBR>(prog, c_begin, c_end, T, rec, st);
+        return launch_ws<G, ChainDynamic>(prog, c_begin, c_end, T, rec, st);
+    }
     if (!no_static) {
         if (chain_matches<ChainGDBR>(prog)) return launch_gc<G, ChainGDBR>(prog, c_begin, c_end, T, n_states, st);
         if (chain_matches<ChainGDR>(prog)) return launch_gc<G, ChainGDR>(prog, c_begin, c_end, T, n_states, st);

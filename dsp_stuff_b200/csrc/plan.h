@@ -109,6 +109,7 @@ struct FirPlan {
     const float2* H;      // [F] spectrum of h in the transform's own output order, pre-scaled by 1/F
     const double* taps;   // [N] reversed taps (f64) for the warm-up path
     float divisor;        // 1/N (Average) or 1 (Balanced), fir.rs:187-190
+    float post_nf;        // != 0: epilogue y = (0.0 + y) / post_nf, the fan-in average of a sink fed only by this node
 };
 // U: [C x (hist_pad + T)] input incl. history; Y: [C x T] output.  started = samples seen before this call.
 int launch_fir(const FirPlan& fp, const float* U, int64_t u_stride, float* Y, int64_t y_stride, int c_begin, int c_end,

@@ -1,8 +1,9 @@
 mkdir -p gpurun_out
-python bench.py --steps 10 --warmup 3 > gpurun_out/bench_target_r1.json 2> gpurun_out/bench_target_r1.err; cat gpurun_out/bench_target_r1.json; tail -2 gpurun_out/bench_target_r1.err
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_target_ref_r1.json 2>/dev/null; cat gpurun_out/bench_target_ref_r1.json
-ncu --metrics gpu__time_duration.sum --clock-control none -s 40 -c 40 --csv --log-file gpurun_out/launches_target_r1.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:fir_fft_kernel -s 3 -c 1 -o gpurun_out/prof_target_fir_r1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:fused_kernel -s 6 -c 1 -o gpurun_out/prof_target_fused_r1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/ncu2.log 2>&1
-tail -1 gpurun_out/ncu1.log gpurun_out/ncu2.log
-nproc; lscpu | grep "Model name"
+python -m pytest tests -m gpu -q 2>&1 | tail -5
+b() { python bench.py "$@" --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>gpurun_out/last.err | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['value']/1e9,2),'Gs/s', round(d['roofline']['whole_step']['frac'],3), round(d['ms_per_step'],4), [(k['kind'], round(k['avg_ms'],4)) for k in d['roofline']['kernels']])" || tail -3 gpurun_out/last.err; }
+echo -n "target: "; b --workload target
+echo -n "target noWS: "; DSPB_NO_WS=1 b --workload target
+for G in 8 16 32; do echo -n "config3 C=4096 G=$G: "; DSPB_FORCE_G=$G b --workload config3 --channels 4096; done
+for G in 2 4 8; do echo -n "config3 C=1024 G=$G: "; DSPB_FORCE_G=$G b --workload config3; done
+echo -n "config3 C=1024 G=4 noWS: "; DSPB_NO_WS=1 DSPB_FORCE_G=4 b --workload config3
+echo -n "config5 C=1024: "; b --workload config5
