@@ -163,11 +163,29 @@ def run_reference(args, spec, alg_bytes, C, n):
                                    f"reference's arithmetic; the Rust reference cannot be built here), {cores} threads"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The JSON line is the ONLY thing on stdout: libraries (NCCL prints its version banner there) were
+    redirected to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
 
 
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     from dsp_stuff_b200 import signals as S
 
     if args.workload not in S.WORKLOADS:
@@ -303,7 +321,7 @@ def main():
             line["gather_to_rank0_ms"] = gather_ms
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(spec, args.cpu_seconds)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -8,8 +8,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdspb200.so")
+DRIVER = os.path.join(HERE, "dspb_run")
 SOURCES = ["engine.cpp", "fused_chain.cu", "fir.cu", "fir_fft.cu"]
-HEADERS = ["plan.h", "json_min.h", os.path.join("..", "..", "include", "dspb200.h")]
+HEADERS = ["plan.h", "json_min.h", "exact_math.cuh", "dspb_run.cpp", os.path.join("..", "..", "include", "dspb200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -46,6 +47,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
         subprocess.check_call(cmd)
         objs.append(obj)
     subprocess.check_call([_nvcc(), "-shared", "-o", LIB] + objs + ARCH + ["-cudart", "static"])
+    # headless C++ driver over the C ABI (links the shared library only)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", DRIVER, os.path.join(CSRC, "dspb_run.cpp"), "-L", HERE,
+                           "-ldspb200", "-Wl,-rpath,$ORIGIN"])
     return LIB
 
 

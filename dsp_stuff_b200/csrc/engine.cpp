@@ -183,6 +183,9 @@ struct dspb_engine {
     std::vector<cudaEvent_t> ev_pool;
     int64_t last_launches = 0;
     int force_G = 0;
+    bool raw_ports = false;  // sub-engine of dspb_node_process: ports carry pre-averaged buffers, no fan-in division
+    struct NodeEngine { dspb_engine* e = nullptr; uint32_t present_mask = 0; };
+    std::map<int64_t, NodeEngine> node_engines;
     bool prof_on = false;
     struct ProfRec { int step; cudaEvent_t a, b; };
     std::vector<ProfRec> prof;
@@ -194,6 +197,7 @@ struct dspb_engine {
         return -1;
     }
     ~dspb_engine() {
+        for (auto& kv : node_engines) delete kv.second.e;
         for (auto& r : prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
         for (auto e : ev_pool) cudaEventDestroy(e);
         if (s_h2d) cudaStreamDestroy(s_h2d);
@@ -324,6 +328,13 @@ struct Lowerer {
     }
     // acc = value (first term: 0.0 + v) or acc += value
     void emit_term(const Value& v, bool first, const std::string& what) {
+        if (e.raw_ports && first && (v.where == Value::VREG || v.where == Value::GLOBAL)) {  // pre-averaged buffer: plain copy
+            Op o = mk(v.where == Value::VREG ? OP_COPYV : OP_COPYG);
+            if (v.where == Value::VREG) o.vreg = (uint8_t)v.id;
+            else o.buf = (uint8_t)buf_slot(v.bind_kind, v.bind_idx);
+            emit(o, "acc = port buffer            ; " + what);
+            return;
+        }
         if (v.where == Value::ZERO || v.where == Value::NONE) {
             if (first) emit(mk(OP_ZERO), "acc = 0                      ; " + what);
             return;  // adding +0.0 changes nothing but the sign of a zero
@@ -354,6 +365,7 @@ struct Lowerer {
                       std::string("link ") + kNodeTypes[e.nodes[k.src]->type].cfg_name + "#" + std::to_string(e.nodes[k.src]->id));
             first = false;
         }
+        if (e.raw_ports) return true;  // dspb_node_process: inputs are already averaged (node.rs:217-222)
         Op d = mk(OP_DIVC);
         set_const_div(d, 0, 1, nf);
         char b[96];
@@ -647,7 +659,7 @@ int Lowerer::lower() {
                 fs.kind = STEP_FIR;
                 fs.fir_node = ni;
                 // A sink fed only by this node: fold its fan-in average into the FIR epilogue
-                if (e.out_links[ni][0].size() == 1) {
+                if (e.out_links[ni][0].size() == 1 && !e.raw_ports) {
                     const int dst = e.links[e.out_links[ni][0][0]].dst;
                     if (e.nodes[dst]->type == T_OUTPUT && e.in_links[dst][0].size() == 1) {
                         fs.fir_out_term = (int)(std::find(e.out_terms.begin(), e.out_terms.end(), dst) - e.out_terms.begin());
@@ -704,10 +716,18 @@ int Lowerer::lower() {
                                           : "acc = v" + std::to_string(vb) + "*r + acc*(1-r)      ; " + tag);
                 values[{ni, 0}] = out_value(0);
             } break;
-            case T_SIGGEN: {
-                err = "signal_gen is not lowered yet";
-                return DSPB_ERR_INVALID;
-            }
+            case T_SIGGEN: {  // nodes/signal_gen.rs:111-130: no signal input, two control ports
+                Op op = mk(OP_SIGGEN);
+                op.mode = (uint8_t)nd.enums[0];
+                ctl_param(op, 0, 0);  // amplitude
+                ctl_param(op, 1, 1);  // frequency
+                op.p[2] = (float)e.cfg.sample_rate;
+                if (alloc_state(op) < 0) return DSPB_ERR_INVALID;
+                char b[160];
+                snprintf(b, sizeof b, "acc = signal_gen[%s](amp=%g, freq=%g)  ; %s", nt.enums[0].variants[nd.enums[0]], nd.f32[0], nd.f32[1], tag.c_str());
+                emit(op, b);
+                values[{ni, 0}] = out_value(0);
+            } break;
             default: {  // single-input effect nodes
                 Op op = mk(OP_END);
                 std::string desc;
@@ -1298,10 +1318,66 @@ int64_t dspb_describe_plan(dspb_engine* e, char* buf, int64_t cap) {
 }
 
 // ---- single-node call: SimpleNode::process on pre-averaged port buffers ----------------------------------------
+// Implemented with a cached one-node sub-engine lowered in "raw ports" mode (no fan-in arithmetic): the node
+// keeps its own state across dspb_node_process calls, independent of the graph-level dspb_process state.
 int dspb_node_process(dspb_engine* e, int64_t node_id, const float* const* port_inputs, const uint8_t* present,
                       float* const* port_outputs, int64_t n, int mem_kind, void* stream) {
-    (void)e; (void)node_id; (void)port_inputs; (void)present; (void)port_outputs; (void)n; (void)mem_kind; (void)stream;
-    return fail(DSPB_ERR_INVALID, "dspb_node_process: not implemented in this build");
+    if (!e || !port_outputs) return fail(DSPB_ERR_INVALID, "null argument");
+    if (e->plan_only) return fail(DSPB_ERR_CUDA, "planning-only engine (device -1) cannot process: there is no CPU fallback");
+    const int i = e->find(node_id);
+    if (i < 0) return fail(DSPB_ERR_UNKNOWN_NODE, "unknown node id %lld", (long long)node_id);
+    Node& src = *e->nodes[i];
+    const NodeType& nt = kNodeTypes[src.type];
+    if (src.type == T_INPUT || src.type == T_OUTPUT) return fail(DSPB_ERR_INVALID, "terminals have no process()");
+    const int n_in = (int)nt.ins.size(), n_out = (int)nt.outs.size();
+    uint32_t mask = 0;
+    for (int p = 0; p < n_in; p++)
+        if (port_inputs && port_inputs[p] && (!present || present[p])) mask |= 1u << p;
+    for (int q = 0; q < n_out; q++)
+        if (!port_outputs[q]) return fail(DSPB_ERR_INVALID, "null output buffer for port '%s'", nt.outs[q]);
+    auto& ne = e->node_engines[node_id];
+    if (!ne.e || ne.present_mask != mask) {
+        delete ne.e;
+        ne.e = nullptr;
+        dspb_engine* sub = nullptr;
+        int r = dspb_engine_create(&e->cfg, &sub);
+        if (r) return r;
+        sub->raw_ports = true;
+        ne.e = sub;
+        ne.present_mask = mask;
+        if ((r = dspb_node_add(sub, nt.cfg_name, 0))) return r;
+        for (int p = 0; p < n_in; p++)
+            if (mask & (1u << p)) {
+                if ((r = dspb_node_add(sub, "input", 1000 + p))) return r;
+                if ((r = dspb_link(sub, 1000 + p, "out", 0, nt.ins[p]))) return r;
+            }
+        for (int q = 0; q < n_out; q++) {
+            if ((r = dspb_node_add(sub, "output", 2000 + q))) return r;
+            if ((r = dspb_link(sub, 0, nt.outs[q], 2000 + q, "in"))) return r;
+        }
+        Node& dst = *sub->nodes[0];
+        dst.f32 = src.f32; dst.enums = src.enums; dst.taps = src.taps; dst.D = src.D;
+        memcpy(dst.bq, src.bq, sizeof dst.bq);
+        if ((r = dspb_compile(sub))) return r;
+    }
+    dspb_engine* sub = ne.e;
+    Node& dst = *sub->nodes[0];
+    // setters on the parent node since the last call: same side effects as on the parent (after_settings_change)
+    if (dst.f32 != src.f32 || dst.enums != src.enums || dst.taps != src.taps || dst.D != src.D) {
+        const bool f32_changed = dst.f32 != src.f32 || dst.D != src.D;
+        const bool taps_changed = dst.taps != src.taps;
+        dst.f32 = src.f32; dst.enums = src.enums; dst.taps = src.taps; dst.D = src.D;
+        memcpy(dst.bq, src.bq, sizeof dst.bq);
+        CUDA_TRY(cudaSetDevice(e->cfg.device));
+        if (f32_changed && dst.type == T_BIQUAD && dst.state.p) CUDA_TRY(cudaMemset(dst.state.p, 0, dst.state.bytes));
+        if (f32_changed && dst.type == T_REVERB) dst.ring_dirty = true;
+        if (taps_changed) dst.fir_dirty = true;
+        sub->lowered = false;
+    }
+    std::vector<const float*> ins;
+    for (int p = 0; p < n_in; p++)
+        if (mask & (1u << p)) ins.push_back(port_inputs[p]);
+    return dspb_process(sub, ins.data(), port_outputs, n, mem_kind, stream);
 }
 
 // ---- saved-graph JSON (runtime.rs:44-48, 94-123, 560-564, 606-612; lib.rs:266-340) ------------------------------

@@ -542,6 +542,76 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
             core.gr = op.p[1];
             run_recurrence<G>(core, acc, c.tc, c.sm_state + op.aux * G);
         } break;
+        case OP_SIGGEN: {  // nodes/signal_gen.rs:55-130: phase accumulates per 128-sample reference block
+            float A[kChunk];
+            if (op.pflags & 1) load16(c.vregs + (op.pv[0] * 4) * kThreads + t, kThreads, A);
+            else {
+#pragma unroll
+                for (int i = 0; i < kChunk; i++) A[i] = op.p[0];
+            }
+            if (mode == 3) {  // Constant: output = amplitude, clock untouched
+#pragma unroll
+                for (int i = 0; i < kChunk; i++) acc[i] = A[i];
+                break;
+            }
+            using Q = Geo<G>;
+            const float sr = op.p[2];
+            const int pos = (c.j & 7) * kChunk;  // first sample of this chunk inside its 128-block
+            float tot[kChunk], total_end;
+            if (op.pflags & 2) {  // frequency from a control port: sequential f32 sum of the block's steps
+                __syncthreads();  // the seven other threads of the block wrote their frequency tiles
+                const float4* fv = c.vregs + (op.pv[1] * 4) * kThreads;
+                float run = 0.0f;
+                const int t0 = t - (c.j & 7);
+                for (int th = 0; th < 8; th++) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const float4 q = fv[k * kThreads + t0 + th];
+                        const float f4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            run = add(run, dv(f4[e], sr));
+                            if (th == (c.j & 7)) tot[4 * k + e] = run;
+                        }
+                    }
+                }
+                total_end = run;
+            } else {
+                const float step = dv(op.p[1], sr);
+                float run = 0.0f;
+                for (int m = 0; m < pos; m++) run = add(run, step);
+#pragma unroll
+                for (int i = 0; i < kChunk; i++) { run = add(run, step); tot[i] = run; }
+                for (int m = pos + kChunk; m < kRefBlock; m++) run = add(run, step);
+                total_end = run;
+            }
+            // clock at the start of this thread's block: state, advanced once per earlier block of the tile.
+            // With a modulated frequency every block has its own total: exchange them through edge[].
+            float4* st = c.sm_state + op.aux * G;
+            float clk = st[c.g].x;
+            const int blk = c.j >> 3;  // block index inside the tile
+            __syncthreads();
+            if ((c.j & 7) == 0) c.edge[t >> 3] = make_float2(total_end, 0.0f);
+            __syncthreads();
+            const int blk0 = (c.g * Q::TPC) >> 3;
+            for (int b = 0; b < blk; b++) clk = fmodf(add(clk, c.edge[blk0 + b].x), 1.0f);
+            const float TAU = 6.28318530717958647692528676655900577f;
+#pragma unroll
+            for (int i = 0; i < kChunk; i++) {
+                float v;
+                if (mode == 0) v = sinf(mul(add(clk, tot[i]), TAU));
+                else if (mode == 1) v = sub(mul(2.0f, fmodf(add(clk, tot[i]), 1.0f)), 1.0f);
+                else v = tot[i] > 0.5f ? 1.0f : -1.0f;  // do_square ignores the clock (signal_gen.rs:93)
+                acc[i] = mul(v, A[i]);
+            }
+            __syncthreads();
+            if (c.j == 0) {  // one thread per channel advances the clock over the valid blocks of this tile
+                float k2 = st[c.g].x;
+                const int nblk = c.tc.valid_f4 / 32;
+                for (int b = 0; b < nblk; b++) k2 = fmodf(add(k2, c.edge[blk0 + b].x), 1.0f);
+                st[c.g].x = k2;
+            }
+        } break;
         default: break;
     }
 }
@@ -907,7 +977,7 @@ int ws_rec_index(const Program& p) {
             if (idx >= 0) return -1;
             idx = i;
         }
-        if (c == OP_HP1) return -1;
+        if (c == OP_HP1 || c == OP_SIGGEN) return -1;
     }
     return idx;
 }
