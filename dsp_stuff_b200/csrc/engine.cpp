@@ -183,6 +183,9 @@ struct dspb_engine {
     std::vector<cudaEvent_t> ev_pool;
     int64_t last_launches = 0;
     int force_G = 0;
+    int dev_chunks = 1;      // device-pointer mode: channel chunks run on separate streams so kernels of different steps overlap
+    std::vector<cudaStream_t> chunk_streams;
+    std::vector<cudaEvent_t> chunk_events;
     bool raw_ports = false;  // sub-engine of dspb_node_process: ports carry pre-averaged buffers, no fan-in division
     struct NodeEngine { dspb_engine* e = nullptr; uint32_t present_mask = 0; };
     std::map<int64_t, NodeEngine> node_engines;
@@ -200,6 +203,8 @@ struct dspb_engine {
         for (auto& kv : node_engines) delete kv.second.e;
         for (auto& r : prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
         for (auto e : ev_pool) cudaEventDestroy(e);
+        for (auto e : chunk_events) cudaEventDestroy(e);
+        for (auto st : chunk_streams) cudaStreamDestroy(st);
         if (s_h2d) cudaStreamDestroy(s_h2d);
         if (s_cmp) cudaStreamDestroy(s_cmp);
         if (s_d2h) cudaStreamDestroy(s_d2h);
@@ -524,24 +529,29 @@ void Lowerer::close_fused() {
     if (e.force_G) G = e.force_G;
     if ((int64_t)kTile / G > min_ring) G = 32;
     cur.G = G;
-    // cp.async prefetch slots: the first streamed global read, and the first comb ring that allows it
+    // Register prefetch (one tile ahead): slot 0 = the first streamed global read, slot 1 = the first comb ring
+    // whose geometry allows it (16-aligned slots; the next tile must not read what this tile writes: D >= 2S).
     const int S = kTile / G;
     P.n_prefetch = 0;
     for (int k = 0; k < kMaxPrefetch; k++) P.pf_buf[k] = P.pf_ring[k] = -1;
-    for (int i = 0; i < P.n_ops && P.n_prefetch < 1; i++)
+    static const bool in_prefetch = !(getenv("DSPB_IN_PREFETCH") && atoi(getenv("DSPB_IN_PREFETCH")) == 0);
+    for (int i = 0; i < P.n_ops && in_prefetch; i++)
         if (P.ops[i].code == OP_LOADG) {
-            P.pf_buf[P.n_prefetch] = P.ops[i].buf;
-            P.ops[i].aux = (uint16_t)(++P.n_prefetch);
+            P.pf_buf[0] = P.ops[i].buf;
+            P.ops[i].aux = 1;
+            P.n_prefetch++;
+            break;
         }
-    for (int i = 0; i < P.n_ops && P.n_prefetch < kMaxPrefetch; i++)
+    static const bool ring_prefetch = !(getenv("DSPB_RING_PREFETCH") && atoi(getenv("DSPB_RING_PREFETCH")) == 0);
+    for (int i = 0; i < P.n_ops && ring_prefetch; i++)
         if (P.ops[i].code == OP_COMB) {
             const Node& rn = *e.nodes[cur.ring_nodes[P.ops[i].aux & 0xff]];
             if ((rn.D & 15) == 0 && rn.D >= 2 * (int64_t)S) {
-                P.pf_ring[P.n_prefetch] = (int16_t)(P.ops[i].aux & 0xff);
-                P.ops[i].aux = (uint16_t)((P.ops[i].aux & 0xff) | ((P.n_prefetch + 1) << 8));
+                P.pf_ring[1] = (int16_t)(P.ops[i].aux & 0xff);
+                P.ops[i].aux = (uint16_t)((P.ops[i].aux & 0xff) | (1 << 8));
                 P.n_prefetch++;
-                break;
             }
+            break;
         }
     int alg = 0;  // ALGORITHMIC bytes per channel-sample of this kernel: 4 per global f32 read/write, 8 per ring
     for (int i = 0; i < P.n_ops; i++) {
@@ -1041,6 +1051,7 @@ int dspb_engine_create(const dspb_config* cfg, dspb_engine** out) {
     if (e->cfg.fir_fft_log2 != 13) { delete e; return fail(DSPB_ERR_INVALID, "fir_fft_log2 must be 13 in this build"); }
     if (e->cfg.fir_mode != FIR_FFT && e->cfg.fir_mode != FIR_DIRECT) { delete e; return fail(DSPB_ERR_INVALID, "fir_mode must be 0 (FFT) or 1 (direct)"); }
     if (const char* g = getenv("DSPB_FORCE_G")) e->force_G = atoi(g);
+    if (const char* g = getenv("DSPB_CHUNKS")) e->dev_chunks = std::max(1, std::min(8, atoi(g)));
     *out = e;
     return DSPB_OK;
 }
@@ -1187,8 +1198,37 @@ int dspb_process(dspb_engine* e, const float* const* inputs, float* const* outpu
             if ((uintptr_t)inputs[i] & 15) return fail(DSPB_ERR_INVALID, "device buffers must be 16-byte aligned");
         for (size_t i = 0; i < n_out; i++)
             if ((uintptr_t)outputs[i] & 15) return fail(DSPB_ERR_INVALID, "device buffers must be 16-byte aligned");
-        r = run_steps(e, inputs, outputs, n, 0, C, (cudaStream_t)stream);
-        if (r) return r;
+        int chunks = e->dev_chunks;
+        if (e->steps.size() < 2 || C < 64 * chunks) chunks = 1;
+        if (chunks <= 1) {
+            r = run_steps(e, inputs, outputs, n, 0, C, (cudaStream_t)stream);
+            if (r) return r;
+        } else {
+            // fork: every chunk's step chain runs on its own stream, so the FIR kernel of chunk k overlaps the
+            // fused kernel of chunk k+1 (both are latency-limited on their own); join back on the caller's stream
+            cudaStream_t cs = (cudaStream_t)stream;
+            while ((int)e->chunk_streams.size() < chunks) {
+                cudaStream_t st2;
+                CUDA_TRY(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+                e->chunk_streams.push_back(st2);
+            }
+            while ((int)e->chunk_events.size() < chunks + 1) {
+                cudaEvent_t ev;
+                CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                e->chunk_events.push_back(ev);
+            }
+            CUDA_TRY(cudaEventRecord(e->chunk_events[chunks], cs));
+            int per = ((C + chunks - 1) / chunks + 31) / 32 * 32;
+            for (int k = 0; k < chunks; k++) {
+                const int c0 = k * per, c1 = std::min(C, c0 + per);
+                if (c0 >= c1) break;
+                CUDA_TRY(cudaStreamWaitEvent(e->chunk_streams[k], e->chunk_events[chunks], 0));
+                r = run_steps(e, inputs, outputs, n, c0, c1, e->chunk_streams[k]);
+                if (r) return r;
+                CUDA_TRY(cudaEventRecord(e->chunk_events[k], e->chunk_streams[k]));
+                CUDA_TRY(cudaStreamWaitEvent(cs, e->chunk_events[k], 0));
+            }
+        }
         advance_state(e, n);
         return DSPB_OK;
     }
@@ -1296,6 +1336,9 @@ int dspb_profile_read(dspb_engine* e, double* ms_total, int64_t* rounds, int cap
     e->prof.clear();
     return (int)e->steps.size();
 }
+
+// debug aid (not part of the public header): phase timing of the warp-specialised kernel, see fused_chain.cu
+int dspb_debug_ws_timing(long long* out8, int clear) { return dspb::ws_timing_read(out8, clear != 0); }
 
 int64_t dspb_describe_plan(dspb_engine* e, char* buf, int64_t cap) {
     if (!e) return 0;

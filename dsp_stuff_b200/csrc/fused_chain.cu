@@ -84,11 +84,20 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_three() { asm volatile("cp.async.wait_group 3;\n" ::: "memory"); }
 
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     float4 r;
     asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
+}
+// Prefetch flavour: the "memory" clobber pins the load where it is written.  Without it the compiler sinks
+// the load down to its first use in the NEXT tile iteration (measured: a full DRAM round trip per tile).
+// The outputs ARE the prefetch registers: going through a temporary float4 makes the compiler emit MOVs
+// right behind the load, which stall on it at once (measured: prefetching was slower than not prefetching).
+__device__ __forceinline__ void ldg_prefetch(const float4* p, float& a, float& b, float& c, float& d) {
+    asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "l"(p) : "memory");
 }
 __device__ __forceinline__ void stg_stream(float4* p, float4 v) {
     asm volatile("st.global.cg.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -127,6 +136,28 @@ struct EnvCore {  // dasp_envelope 0.11.0 Detector<f32, Peak<FullWave>>::next, d
 // and the lane = channel accesses (rows padded by 4 floats) bank-conflict free.
 __device__ __forceinline__ int swz(int m) { return (m & ~3) | ((m & 3) ^ ((m >> 3) & 3)); }
 
+
+// Sequential feedback loop over one tile row (lane = channel): `valid_f4` float4s at swizzled slots.  Loads
+// run two float4s ahead of their use and are unconditional (clamped index).
+template <class Core>
+__device__ __forceinline__ void recurrence_row(Core& core, float4* r, int valid_f4) {
+    const int last = valid_f4 - 1;
+    float4 a = r[swz(0)];
+    float4 b = r[swz(min(1, last))];
+#pragma unroll 4
+    for (int m = 0; m < valid_f4; m++) {
+        const float4 nxt = r[swz(min(m + 2, last))];
+        float4 x = a;
+        x.x = core.step(x.x);
+        x.y = core.step(x.y);
+        x.z = core.step(x.z);
+        x.w = core.step(x.w);
+        r[swz(m)] = x;
+        a = b;
+        b = nxt;
+    }
+}
+
 template <int G>
 struct Geo {
     static constexpr int S = kTile / G;        // samples per channel per tile
@@ -153,17 +184,7 @@ __device__ __forceinline__ void run_recurrence(Core core, float (&v)[kChunk], co
         float4* r = reinterpret_cast<float4*>(c.tile + lane * Q::ROW);
         float4 s = st[lane];
         core.load(s);
-        float4 x = r[swz(0)];
-        for (int m = 0; m < c.valid_f4; m++) {
-            float4 nx = x;
-            if (m + 1 < c.valid_f4) nx = r[swz(m + 1)];
-            x.x = core.step(x.x);
-            x.y = core.step(x.y);
-            x.z = core.step(x.z);
-            x.w = core.step(x.w);
-            r[swz(m)] = x;
-            x = nx;
-        }
+        recurrence_row(core, r, c.valid_f4);
         core.save(s);
         st[lane] = s;
     }
@@ -218,25 +239,38 @@ struct Ctx {
     int t, g, j, ch, j_last;
     bool ch_ok, active;
 
-    // stage slot s for tile `ti` (thread-private, so no barrier is needed around it)
-    __device__ __forceinline__ void issue_prefetch(int s, long long ti) const {
+    // Register prefetch, one tile ahead: right after a tile's input chunk (slot 0: the first streamed global
+    // read) or ring chunk (slot 1: the first eligible comb ring) has been copied out of pf_*, the loads for
+    // the next tile are issued straight into the same registers and stay in flight while this tile computes.
+    // (An earlier version staged these through shared memory with cp.async; its 16 extra shared-memory
+    // instructions per thread and tile clogged the SM-wide LSU queue the sequential R warp depends on.)
+    __device__ __forceinline__ const float* prefetch_src(int s, long long ti, bool& ok) const {
         using Q = Geo<G>;
         const long long m0 = ti * Q::S + (long long)j * kChunk;
-        if (ch_ok && ti < n_tiles && m0 < T) {
-            const float* src;
-            if (prog->pf_buf[s] >= 0) {
-                const BufDesc& b = prog->bufs[prog->pf_buf[s]];
-                src = b.base + (long long)ch * b.row_stride + m0;
-            } else {
-                const RingDesc& r = prog->rings[prog->pf_ring[s]];
-                src = r.base + (long long)ch * r.D + (r.pos + m0) % r.D;
-            }
-            float4* dst = stage + (s * 4) * kThreads + t;
-#pragma unroll
-            for (int k = 0; k < 4; k++) cp_async16(dst + k * kThreads, src + 4 * k);
+        ok = ch_ok && ti < n_tiles && m0 < T;
+        if (s == 0) {
+            const BufDesc& b = prog->bufs[prog->pf_buf[0]];
+            return b.base + (long long)ch * b.row_stride + m0;
         }
-        cp_async_commit();
+        const RingDesc& r = prog->rings[prog->pf_ring[1]];
+        return r.base + (long long)ch * r.D + (r.pos + m0) % r.D;
     }
+    // The destination must be a register array of the kernel itself (like `acc`), NOT a member of this struct:
+    // the struct lives in local memory inside the interpreter loop, and a load whose result is stored to the
+    // stack right away stalls on it immediately (measured: the "prefetch" then hides nothing).
+    __device__ __forceinline__ void prefetch(int slot, long long ti, float (&pf)[kChunk]) const {
+        bool ok;
+        const float4* p = reinterpret_cast<const float4*>(prefetch_src(slot, ti, ok));
+        if (ok) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) ldg_prefetch(p + k, pf[4 * k], pf[4 * k + 1], pf[4 * k + 2], pf[4 * k + 3]);
+        }
+    }
+};
+
+// the two prefetch register sets of a thread (input chunk, ring chunk of the next tile)
+struct Pf {
+    float in[kChunk], ring[kChunk];
 };
 
 // One op of the segment program on this thread's 16 samples.  `code`, `mode` and `pre` are
@@ -245,7 +279,7 @@ struct Ctx {
 // pre & 2: acc /= nf (node.rs:189-191) with the divisor in p[4], its reciprocal in p[5].
 template <int G>
 __device__ __forceinline__ void exec_op(const int code, const int mode, const int pre, const Op& op, const Ctx<G>& c,
-                                        float (&acc)[kChunk]) {
+                                        float (&acc)[kChunk], Pf& pf) {
     const Program& prog = *c.prog;
     const int t = c.t;
     if (pre & 1) {
@@ -265,9 +299,12 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
             float v[kChunk];
 #pragma unroll
             for (int i = 0; i < kChunk; i++) v[i] = 0.0f;
-            if (op.aux) {  // staged by cp.async; refill the slot for the next tile right away
-                if (c.active) load16(c.stage + ((op.aux - 1) * 4) * kThreads + t, kThreads, v);
-                c.issue_prefetch(op.aux - 1, c.tile_i + 1);
+            if (op.aux) {  // prefetched into registers one tile ago; request the next tile right away
+                if (c.active) {
+#pragma unroll
+                    for (int i = 0; i < kChunk; i++) v[i] = pf.in[i];
+                }
+                c.prefetch(0, c.tile_i + 1, pf.in);
             } else if (c.active) {
                 const BufDesc& b = prog.bufs[op.buf];
                 const float4* p = reinterpret_cast<const float4*>(b.base + (long long)c.ch * b.row_stride + c.n0);
@@ -468,8 +505,11 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
 #pragma unroll
                 for (int i = 0; i < kChunk; i++) old[i] = 0.0f;
                 if (pslot) {
-                    if (c.active) load16(c.stage + ((pslot - 1) * 4) * kThreads + t, kThreads, old);
-                    c.issue_prefetch(pslot - 1, c.tile_i + 1);
+                    if (c.active) {
+#pragma unroll
+                        for (int i = 0; i < kChunk; i++) old[i] = pf.ring[i];
+                    }
+                    c.prefetch(1, c.tile_i + 1, pf.ring);
                 } else if (c.active) {
                     const float4* p = reinterpret_cast<const float4*>(rrow + slot);
 #pragma unroll
@@ -657,16 +697,16 @@ struct ChainCopy {  // G -> (/nf) -> store   (the segment after a Fir node)
 };
 
 template <int G, class Chain, int I>
-__device__ __forceinline__ void run_static(const Program& prog, const Ctx<G>& c, float (&acc)[kChunk]) {
+__device__ __forceinline__ void run_static(const Program& prog, const Ctx<G>& c, float (&acc)[kChunk], Pf& pf) {
     if constexpr (I < Chain::n) {
         constexpr int s = Chain::sig(I);
-        exec_op<G>(s & 0xff, (s >> 8) & 0xff, (s >> 16) & 0xff, prog.ops[I], c, acc);
-        run_static<G, Chain, I + 1>(prog, c, acc);
+        exec_op<G>(s & 0xff, (s >> 8) & 0xff, (s >> 16) & 0xff, prog.ops[I], c, acc, pf);
+        run_static<G, Chain, I + 1>(prog, c, acc, pf);
     }
 }
 
 template <int G, class Chain>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 2)
 fused_kernel(const __grid_constant__ Program prog, int c_begin, int c_end, long long T, int n_states, int n_sm) {
     using Q = Geo<G>;
     extern __shared__ float4 smem4[];
@@ -685,7 +725,7 @@ fused_kernel(const __grid_constant__ Program prog, int c_begin, int c_end, long 
     c.edge = reinterpret_cast<float2*>(c.sm_state + kMaxStates * G);     // [256] chunk-edge samples
     float* tile = reinterpret_cast<float*>(c.edge + kThreads);
     c.stage = reinterpret_cast<float4*>(tile + (prog.needs_tile ? G * Q::ROW : 0));  // [n_prefetch][4][256]
-    c.vregs = c.stage + prog.n_prefetch * 4 * kThreads;                              // [n_vregs][4][256]
+    c.vregs = c.stage;                                                               // [n_vregs][4][256]
 
     for (int i = t; i < n_states * G; i += kThreads) {
         int s = i / G, cc = c_begin + blockIdx.x * G + (i % G);
@@ -699,7 +739,11 @@ fused_kernel(const __grid_constant__ Program prog, int c_begin, int c_end, long 
     // co-resident CTAs (bid, bid + n_sm, ...) put their sequential warp on different SM sub-partitions
     c.tc.rec_warp = 7 - (int)((blockIdx.x / (unsigned)n_sm) & 3u);
 
-    for (int s = 0; s < prog.n_prefetch; s++) c.issue_prefetch(s, 0);
+    Pf pf;
+#pragma unroll
+    for (int i = 0; i < kChunk; i++) pf.in[i] = pf.ring[i] = 0.0f;
+    if (prog.pf_buf[0] >= 0) c.prefetch(0, 0, pf.in);
+    if (prog.pf_ring[1] >= 0) c.prefetch(1, 0, pf.ring);
     __syncthreads();
 
     for (long long tile_i = 0; tile_i < c.n_tiles; tile_i++) {
@@ -711,22 +755,20 @@ fused_kernel(const __grid_constant__ Program prog, int c_begin, int c_end, long 
         c.j_last = c.tc.valid_f4 / 4 - 1;  // thread holding the last valid chunk of each channel
 
         __syncthreads();  // ring / tile hazards across tiles
-        cp_async_wait_all();
 
         float acc[kChunk];
 #pragma unroll
         for (int i = 0; i < kChunk; i++) acc[i] = 0.0f;
 
         if constexpr (Chain::n > 0) {
-            run_static<G, Chain, 0>(prog, c, acc);
+            run_static<G, Chain, 0>(prog, c, acc, pf);
         } else {
             for (int ip = 0; ip < prog.n_ops; ip++) {
                 const Op& op = prog.ops[ip];
-                exec_op<G>(op.code, op.mode, op.pre, op, c, acc);
+                exec_op<G>(op.code, op.mode, op.pre, op, c, acc, pf);
             }
         }
     }
-    cp_async_wait_all();
     __syncthreads();
     for (int i = t; i < n_states * G; i += kThreads) {
         int s = i / G, cc = c_begin + blockIdx.x * G + (i % G);
@@ -742,7 +784,19 @@ fused_kernel(const __grid_constant__ Program prog, int c_begin, int c_end, long 
 // for tile i (and hand tile buffer i&1 to R), then the ops after it for tile i-1 (once R is done with it),
 // so the sequential 12-cycle-per-sample chain is hidden behind elementwise work of neighbouring tiles.
 // Hand-offs use named barriers (bar.arrive / bar.sync with the 288-thread count).
-constexpr int kWsThreads = kThreads + 32;
+// NR recurrence warps (one per SM sub-partition) split the CTA's channels: each R warp only gets its fair
+// share of its scheduler's issue slots next to the always-ready E warps, so two of them on different
+// sub-partitions advance the recurrences twice as fast.
+// Optional phase timing (build with -DDSPB_WS_TIMING): summed clock64 deltas of CTA 0:
+// [0] R waits for FULL  [1] R loop  [2] E pre-ops  [3] E waits for DONE  [4] E post-ops  [5] E waits EONLY
+__device__ long long g_ws_timing[8];
+constexpr int kNR = 1;
+// Measured (tests/cuda/rec_microbench.cu, DSPB_WS_TIMING): an R warp alone takes 14 cycles per step and 36-50
+// inside this kernel, but it is never the bottleneck -- the elementwise warps are (E never waits for DONE, R
+// idles ~30 % of the time waiting for FULL).  Giving R its own SM sub-partition or a second R warp changed
+// nothing, so the layout stays simple: E warps first, R warp last.
+constexpr int kWsThreads = kThreads + 32 * kNR;
+constexpr int kWsLaunchThreads = kWsThreads;
 enum { BAR_FULL0 = 1, BAR_FULL1 = 2, BAR_DONE0 = 3, BAR_DONE1 = 4, BAR_EONLY = 5 };
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -750,7 +804,7 @@ __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.ar
 template <int G, class Core>
 __device__ __forceinline__ void ws_recurrence_warp(Core core, float* tiles, const float4* st_in, float4* st_out, int lane,
                                                    bool ch_ok, long long n_tiles, long long T) {
-    using Q = Geo<G>;
+    using Q = Geo<G>;  // `lane` is the channel index inside the CTA (or >= G for idle lanes)
     float4 s = make_float4(0, 0, 0, 0);
     if (lane < G && ch_ok) s = *st_in;
     core.load(s);
@@ -761,17 +815,7 @@ __device__ __forceinline__ void ws_recurrence_warp(Core core, float* tiles, cons
         bar_sync(BAR_FULL0 + b, kWsThreads);
         if (lane < G) {
             float4* r = reinterpret_cast<float4*>(tiles + b * (G * Q::ROW) + lane * Q::ROW);
-            float4 x = r[swz(0)];
-            for (int m = 0; m < valid_f4; m++) {
-                float4 nx = x;
-                if (m + 1 < valid_f4) nx = r[swz(m + 1)];
-                x.x = core.step(x.x);
-                x.y = core.step(x.y);
-                x.z = core.step(x.z);
-                x.w = core.step(x.w);
-                r[swz(m)] = x;
-                x = nx;
-            }
+            recurrence_row(core, r, valid_f4);
         }
         __threadfence_block();  // bar.arrive alone orders nothing: make the tile visible first
         __syncwarp();
@@ -784,20 +828,20 @@ __device__ __forceinline__ void ws_recurrence_warp(Core core, float* tiles, cons
 }
 
 template <int G, class Chain, int I, int END>
-__device__ __forceinline__ void run_static_range(const Program& prog, const Ctx<G>& c, float (&acc)[kChunk]) {
+__device__ __forceinline__ void run_static_range(const Program& prog, const Ctx<G>& c, float (&acc)[kChunk], Pf& pf) {
     if constexpr (I < END) {
         constexpr int s = Chain::sig(I);
-        exec_op<G>(s & 0xff, (s >> 8) & 0xff, (s >> 16) & 0xff, prog.ops[I], c, acc);
-        run_static_range<G, Chain, I + 1, END>(prog, c, acc);
+        exec_op<G>(s & 0xff, (s >> 8) & 0xff, (s >> 16) & 0xff, prog.ops[I], c, acc, pf);
+        run_static_range<G, Chain, I + 1, END>(prog, c, acc, pf);
     }
 }
 
 template <int G, class Chain>
-__global__ void __launch_bounds__(kWsThreads, 3)
+__global__ void __launch_bounds__(kWsLaunchThreads, 2)
 fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, long long T, int n_sm, int rec_index) {
     using Q = Geo<G>;
     extern __shared__ float4 smem4[];
-    const int t = threadIdx.x;
+    const int t = threadIdx.x;  // t < kThreads: elementwise thread, else R-warp thread
     // shared memory: [G] x-state (float2) | edge[256] | tiles[2][G*ROW] | stage
     float2* xstate = reinterpret_cast<float2*>(smem4);
     float2* edge = xstate + 32;
@@ -809,8 +853,10 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
     float* stp = prog.states[rop.aux];
     (void)n_sm;
 
-    if (t >= kThreads) {  // ---------------- R warp ----------------
-        const int lane = t - kThreads;
+    if (t >= kThreads) {  // ---------------- R warps ----------------
+        constexpr int GP = (G + kNR - 1) / kNR;  // channels per R warp
+        const int rw = (t - kThreads) >> 5, rl = t & 31;
+        const int lane = rl < GP ? rw * GP + rl : G;  // channel inside the CTA; G = idle lane
         const int ch = c_begin + blockIdx.x * G + lane;
         const bool ok = lane < G && ch < c_end;
         const float4* sin = reinterpret_cast<const float4*>(stp) + (ok ? ch : 0);
@@ -826,18 +872,20 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
                 const int b = (int)(i & 1);
                 const long long rem = T - i * QQ::S;
                 const int valid_f4 = (int)((rem < QQ::S ? rem : QQ::S) / 4);
+#ifdef DSPB_WS_TIMING
+                long long tq0 = clock64();
+#endif
                 bar_sync(BAR_FULL0 + b, kWsThreads);
+#ifdef DSPB_WS_TIMING
+                long long tq1 = clock64();
+#endif
                 if (lane < G) {
                     float4* r = reinterpret_cast<float4*>(tiles + b * (G * QQ::ROW) + lane * QQ::ROW);
-                    float4 x = r[swz(0)];
-                    for (int m = 0; m < valid_f4; m++) {
-                        float4 nx = x;
-                        if (m + 1 < valid_f4) nx = r[swz(m + 1)];
-                        x.x = core.step(x.x); x.y = core.step(x.y); x.z = core.step(x.z); x.w = core.step(x.w);
-                        r[swz(m)] = x;
-                        x = nx;
-                    }
+                    recurrence_row(core, r, valid_f4);
                 }
+#ifdef DSPB_WS_TIMING
+                if (blockIdx.x == 0 && t == kThreads) { long long tq2 = clock64(); g_ws_timing[0] += tq1 - tq0; g_ws_timing[1] += tq2 - tq1; }
+#endif
                 __threadfence_block();
                 __syncwarp();
                 bar_arrive(BAR_DONE0 + b, kWsThreads);
@@ -875,7 +923,11 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
         const int ch = c_begin + blockIdx.x * G + t;
         xstate[t] = (rcode == OP_BIQUAD && ch < c_end) ? *reinterpret_cast<const float2*>(stp + 4 * (long long)ch) : make_float2(0.f, 0.f);
     }
-    for (int s = 0; s < prog.n_prefetch; s++) c.issue_prefetch(s, 0);
+    Pf pf;
+#pragma unroll
+    for (int i = 0; i < kChunk; i++) pf.in[i] = pf.ring[i] = 0.0f;
+    if (prog.pf_buf[0] >= 0) c.prefetch(0, 0, pf.in);
+    if (prog.pf_ring[1] >= 0) c.prefetch(1, 0, pf.ring);
     bar_sync(BAR_EONLY, kThreads);
 
     auto set_tile = [&](long long ti) {
@@ -888,16 +940,29 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
     };
 
     for (long long i = 0; i <= n_tiles; i++) {
+#ifdef DSPB_WS_TIMING
+        long long tb0 = clock64();
+        long long tp1 = 0, tp2 = 0;
+#endif
         bar_sync(BAR_EONLY, kThreads);  // ring hazards across tiles, edge[] reuse
+#ifdef DSPB_WS_TIMING
+        if (blockIdx.x == 0 && t == 0) g_ws_timing[5] += clock64() - tb0;
+#endif
         cp_async_wait_all();
         float acc[kChunk];
+#ifdef DSPB_WS_TIMING
+        long long te0 = clock64(), te1 = te0, te2 = te0;
+#endif
         if (i < n_tiles) {  // ---- ops before the recurrence, tile i ----
             set_tile(i);
 #pragma unroll
             for (int k = 0; k < kChunk; k++) acc[k] = 0.0f;
-            if constexpr (Chain::n > 0) run_static_range<G, Chain, 0, Chain::rec>(prog, c, acc);
+            if constexpr (Chain::n > 0) run_static_range<G, Chain, 0, Chain::rec>(prog, c, acc, pf);
             else
-                for (int ip = 0; ip < rec_index; ip++) exec_op<G>(prog.ops[ip].code, prog.ops[ip].mode, prog.ops[ip].pre, prog.ops[ip], c, acc);
+                for (int ip = 0; ip < rec_index; ip++) exec_op<G>(prog.ops[ip].code, prog.ops[ip].mode, prog.ops[ip].pre, prog.ops[ip], c, acc, pf);
+#ifdef DSPB_WS_TIMING
+            tp1 = clock64();
+#endif
             // the recurrence op's own prologue and feed-forward part
             const int rpre = Chain::n > 0 ? ((Chain::sig(Chain::rec) >> 16) & 0xff) : rop.pre;
             if (rpre & 1) {
@@ -909,6 +974,9 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
                 const float b0 = rop.p[0], b1 = rop.p[1], b2 = rop.p[2];
                 edge[t] = make_float2(acc[14], acc[15]);
                 bar_sync(BAR_EONLY, kThreads);
+#ifdef DSPB_WS_TIMING
+                tp2 = clock64();
+#endif
                 float xm1, xm2;
                 if (c.j == 0) { const float2 s2 = xstate[c.g]; xm1 = s2.x; xm2 = s2.y; }
                 else { const float2 e = edge[t - 1]; xm2 = e.x; xm1 = e.y; }
@@ -940,9 +1008,15 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
             __threadfence_block();
             bar_arrive(BAR_FULL0 + (int)(i & 1), kWsThreads);
         }
+#ifdef DSPB_WS_TIMING
+        te1 = clock64();
+#endif
         if (i >= 1) {  // ---- ops after the recurrence, tile i-1 ----
             const int b = (int)((i - 1) & 1);
             bar_sync(BAR_DONE0 + b, kWsThreads);
+#ifdef DSPB_WS_TIMING
+            te2 = clock64();
+#endif
             set_tile(i - 1);
             const float4* row = reinterpret_cast<const float4*>(tiles + b * (G * Q::ROW) + c.g * Q::ROW);
 #pragma unroll
@@ -950,12 +1024,15 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
                 const float4 q = row[4 * c.j + (k ^ ((c.j >> 1) & 3))];
                 acc[4 * k] = q.x; acc[4 * k + 1] = q.y; acc[4 * k + 2] = q.z; acc[4 * k + 3] = q.w;
             }
-            if constexpr (Chain::n > 0) run_static_range<G, Chain, Chain::rec + 1, Chain::n>(prog, c, acc);
+            if constexpr (Chain::n > 0) run_static_range<G, Chain, Chain::rec + 1, Chain::n>(prog, c, acc, pf);
             else
-                for (int ip = rec_index + 1; ip < prog.n_ops; ip++) exec_op<G>(prog.ops[ip].code, prog.ops[ip].mode, prog.ops[ip].pre, prog.ops[ip], c, acc);
+                for (int ip = rec_index + 1; ip < prog.n_ops; ip++) exec_op<G>(prog.ops[ip].code, prog.ops[ip].mode, prog.ops[ip].pre, prog.ops[ip], c, acc, pf);
         }
+#ifdef DSPB_WS_TIMING
+        if (blockIdx.x == 0 && t == 0) { long long te3 = clock64(); g_ws_timing[2] += te1 - te0; g_ws_timing[3] += te2 - te1; g_ws_timing[4] += te3 - te2;
+            if (tp1) { g_ws_timing[6] += tp1 - te0; g_ws_timing[7] += tp2 - tp1; } }
+#endif
     }
-    cp_async_wait_all();
     bar_sync(BAR_EONLY, kThreads);
     if (rcode == OP_BIQUAD && t < G) {
         const int ch = c_begin + blockIdx.x * G + t;
@@ -963,9 +1040,20 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
     }
 }
 
+}  // namespace
+int ws_timing_read(long long* out, bool clear) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_ws_timing, 8 * sizeof(long long));
+    if (e == cudaSuccess && clear) {
+        long long z[8] = {0};
+        e = cudaMemcpyToSymbol(g_ws_timing, z, sizeof z);
+    }
+    return (int)e;
+}
+namespace {
 int ws_smem_bytes(const Program& prog, int G) {
     const int S = kTile / G;
-    return 32 * 8 + kThreads * 8 + 2 * G * (S + 4) * 4 + prog.n_prefetch * kTile * 4;
+    (void)prog;
+    return 32 * 8 + kThreads * 8 + 2 * G * (S + 4) * 4;
 }
 // index of the single recurrence op if the program qualifies for the warp-specialised kernel, else -1
 int ws_rec_index(const Program& p) {
@@ -992,7 +1080,7 @@ int launch_ws(const Program& prog, int c_begin, int c_end, int64_t T, int rec_in
         configured = smem;
     }
     const int n_cta = (c_end - c_begin + G - 1) / G;
-    fused_kernel_ws<G, Chain><<<n_cta, kWsThreads, smem, st>>>(prog, c_begin, c_end, (long long)T, 148, rec_index);
+    fused_kernel_ws<G, Chain><<<n_cta, kWsLaunchThreads, smem, st>>>(prog, c_begin, c_end, (long long)T, 148, rec_index);
     return (int)cudaGetLastError();
 }
 
@@ -1081,7 +1169,6 @@ int fused_smem_bytes(const Program& prog, int G) {
     const int S = kTile / G;
     size_t b = (size_t)kMaxStates * G * 16 + (size_t)kThreads * 8;
     if (prog.needs_tile) b += (size_t)G * (S + 4) * 4;
-    b += (size_t)prog.n_prefetch * kTile * 4;
     b += (size_t)prog.n_vregs * kTile * 4;
     return (int)b;
 }

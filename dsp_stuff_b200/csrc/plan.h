@@ -99,6 +99,8 @@ int launch_fused(const Program& prog, int G, int c_begin, int c_end, int64_t T, 
 int fused_smem_bytes(const Program& prog, int G);
 // Enumerates all 2^32 dividends on the device; *mismatches == 0 proves div_const exact for divisor b.
 int verify_const_div(float b, float r, unsigned long long* mismatches);
+// debug: summed clock64 phase timings of the warp-specialised kernel (only with -DDSPB_WS_TIMING)
+int ws_timing_read(long long* out8, bool clear);
 
 enum FirMode { FIR_FFT = 0, FIR_DIRECT = 1 };
 struct FirPlan {
