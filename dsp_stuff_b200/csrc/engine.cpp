@@ -546,7 +546,7 @@ void Lowerer::close_fused() {
     for (int i = 0; i < P.n_ops && ring_prefetch; i++)
         if (P.ops[i].code == OP_COMB) {
             const Node& rn = *e.nodes[cur.ring_nodes[P.ops[i].aux & 0xff]];
-            if ((rn.D & 15) == 0 && rn.D >= 2 * (int64_t)S) {
+            if ((rn.D & (kChunk - 1)) == 0 && rn.D >= 2 * (int64_t)S) {
                 P.pf_ring[1] = (int16_t)(P.ops[i].aux & 0xff);
                 P.ops[i].aux = (uint16_t)((P.ops[i].aux & 0xff) | (1 << 8));
                 P.n_prefetch++;

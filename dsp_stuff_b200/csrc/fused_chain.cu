@@ -31,6 +31,12 @@ __device__ __forceinline__ float clipf(float s) { return s < -1.0f ? -1.0f : (s 
 __device__ __forceinline__ float signumf(float x) { return x != x ? x : copysignf(1.0f, x); }
 __device__ __forceinline__ float clamp01(float x) { return x < 0.0f ? 0.0f : (x > 1.0f ? 1.0f : x); }
 
+constexpr int kF4 = kChunk / 4;            // float4s per thread chunk
+constexpr int kBlk = kRefBlock / kChunk;    // threads per 128-sample reference block
+static_assert(kF4 == 2 || kF4 == 4, "swizzles below are written for 8 or 16 samples per thread");
+// swizzle of a thread's float4 slots inside a transposed tile row (conflict-free for 8 consecutive lanes)
+__device__ __forceinline__ int sw_of(int j) { return kF4 == 4 ? ((j >> 1) & 3) : ((j >> 2) & 1); }
+
 enum DistortMode { HardClip, SoftClip, Tanh, RecipSoftClip, Fuzz, Sin, Atan, Square, Chebyshev4 };
 
 // Per-sample level (control port connected): kept out of line so the rare path costs no registers.
@@ -66,15 +72,14 @@ __device__ __noinline__ float overdrive_generic(float x, float b, float dr, floa
     return mul(add(mul(dr, d), mul(sub(1.0f, dr), x)), l);
 }
 
-// max over the 8 consecutive threads (= one 128-sample reference block) of |v| under
+// max over the kBlk consecutive threads (= one 128-sample reference block) of |v| under
 // f32::total_cmp: non-negative floats and NaNs order like their bit patterns.
 __device__ __forceinline__ float block128_max_abs(const float (&v)[kChunk]) {
     unsigned m = 0;
 #pragma unroll
     for (int i = 0; i < kChunk; i++) m = max(m, __float_as_uint(fabsf(v[i])));
-    m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    m = max(m, __shfl_xor_sync(0xffffffffu, m, 4));
+#pragma unroll
+    for (int d = 1; d < kBlk; d <<= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
     return __uint_as_float(m);
 }
 
@@ -134,7 +139,7 @@ struct EnvCore {  // dasp_envelope 0.11.0 Detector<f32, Peak<FullWave>>::next, d
 // Swizzled float4 slot of logical float4 index m inside a tile row: thread j writes its four
 // float4s to 4j + (k ^ ((j>>1)&3)), which makes both the time-parallel accesses (8 lanes, stride 64 B)
 // and the lane = channel accesses (rows padded by 4 floats) bank-conflict free.
-__device__ __forceinline__ int swz(int m) { return (m & ~3) | ((m & 3) ^ ((m >> 3) & 3)); }
+__device__ __forceinline__ int swz(int m) { return (m & ~(kF4 - 1)) | ((m & (kF4 - 1)) ^ sw_of(m / kF4)); }
 
 
 // Sequential feedback loop over one tile row (lane = channel): `valid_f4` float4s at swizzled slots.  Loads
@@ -176,8 +181,8 @@ __device__ __forceinline__ void run_recurrence(Core core, float (&v)[kChunk], co
     using Q = Geo<G>;
     float4* row = reinterpret_cast<float4*>(c.tile + c.g * Q::ROW);
 #pragma unroll
-    for (int k = 0; k < 4; k++)
-        row[4 * c.j + (k ^ ((c.j >> 1) & 3))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    for (int k = 0; k < kF4; k++)
+        row[kF4 * c.j + (k ^ sw_of(c.j))] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     if ((threadIdx.x >> 5) == c.rec_warp && lane < G && c.valid_f4 > 0) {  // strictly sequential in time
@@ -190,22 +195,22 @@ __device__ __forceinline__ void run_recurrence(Core core, float (&v)[kChunk], co
     }
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        float4 q = row[4 * c.j + (k ^ ((c.j >> 1) & 3))];
+    for (int k = 0; k < kF4; k++) {
+        float4 q = row[kF4 * c.j + (k ^ sw_of(c.j))];
         v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
     }
 }
 
 __device__ __forceinline__ void load16(const float4* s, int stride, float (&v)[kChunk]) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < kF4; k++) {
         float4 q = s[k * stride];
         v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
     }
 }
 __device__ __forceinline__ void store16(float4* s, int stride, const float (&v)[kChunk]) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) s[k * stride] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    for (int k = 0; k < kF4; k++) s[k * stride] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
 }
 
 // acc[i] /= b for a host-known divisor: exact fast path, IEEE division when the chunk holds zeros,
@@ -263,7 +268,7 @@ struct Ctx {
         const float4* p = reinterpret_cast<const float4*>(prefetch_src(slot, ti, ok));
         if (ok) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) ldg_prefetch(p + k, pf[4 * k], pf[4 * k + 1], pf[4 * k + 2], pf[4 * k + 3]);
+            for (int k = 0; k < kF4; k++) ldg_prefetch(p + k, pf[4 * k], pf[4 * k + 1], pf[4 * k + 2], pf[4 * k + 3]);
         }
     }
 };
@@ -309,7 +314,7 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
                 const BufDesc& b = prog.bufs[op.buf];
                 const float4* p = reinterpret_cast<const float4*>(b.base + (long long)c.ch * b.row_stride + c.n0);
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
+                for (int k = 0; k < kF4; k++) {
                     float4 q = ldg_stream(p + k);
                     v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
                 }
@@ -323,20 +328,20 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
         case OP_COPYV:
         case OP_ADD: {
             float v[kChunk];
-            load16(c.vregs + (op.vreg * 4) * kThreads + t, kThreads, v);
+            load16(c.vregs + (op.vreg * kF4) * kThreads + t, kThreads, v);
 #pragma unroll
             for (int i = 0; i < kChunk; i++)
                 acc[i] = code == OP_COPYV ? v[i] : add(code == OP_LOADV ? 0.0f : acc[i], v[i]);
         } break;
         case OP_SAVEV: {
-            store16(c.vregs + (op.vreg * 4) * kThreads + t, kThreads, acc);
+            store16(c.vregs + (op.vreg * kF4) * kThreads + t, kThreads, acc);
         } break;
         case OP_STOREG: {
             if (c.active) {
                 const BufDesc& b = prog.bufs[op.buf];
                 float4* p = reinterpret_cast<float4*>(b.base + (long long)c.ch * b.row_stride + c.n0);
 #pragma unroll
-                for (int k = 0; k < 4; k++) stg_stream(p + k, make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]));
+                for (int k = 0; k < kF4; k++) stg_stream(p + k, make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]));
             }
         } break;
         case OP_MODMAP: {  // lib.rs:138-146; (x + 1) / 2 == (x + 1) * 0.5 exactly
@@ -347,7 +352,7 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
         case OP_GAIN: {
             if (op.pflags & 1) {
                 float P[kChunk];
-                load16(c.vregs + (op.pv[0] * 4) * kThreads + t, kThreads, P);
+                load16(c.vregs + (op.pv[0] * kF4) * kThreads + t, kThreads, P);
 #pragma unroll
                 for (int i = 0; i < kChunk; i++) acc[i] = mul(acc[i], P[i]);
             } else {
@@ -423,7 +428,7 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
                 break;
             }
             float P[kChunk];
-            if (op.pflags & 1) load16(c.vregs + (op.pv[0] * 4) * kThreads + t, kThreads, P);
+            if (op.pflags & 1) load16(c.vregs + (op.pv[0] * kF4) * kThreads + t, kThreads, P);
             else {
 #pragma unroll
                 for (int i = 0; i < kChunk; i++) P[i] = op.p[0];
@@ -452,9 +457,9 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
                 float B[kChunk], D[kChunk], L[kChunk];
 #pragma unroll
                 for (int i = 0; i < kChunk; i++) { B[i] = op.p[0]; D[i] = op.p[1]; L[i] = op.p[2]; }
-                if (op.pflags & 1) load16(c.vregs + (op.pv[0] * 4) * kThreads + t, kThreads, B);
-                if (op.pflags & 2) load16(c.vregs + (op.pv[1] * 4) * kThreads + t, kThreads, D);
-                if (op.pflags & 4) load16(c.vregs + (op.pv[2] * 4) * kThreads + t, kThreads, L);
+                if (op.pflags & 1) load16(c.vregs + (op.pv[0] * kF4) * kThreads + t, kThreads, B);
+                if (op.pflags & 2) load16(c.vregs + (op.pv[1] * kF4) * kThreads + t, kThreads, D);
+                if (op.pflags & 4) load16(c.vregs + (op.pv[2] * kF4) * kThreads + t, kThreads, L);
 #pragma unroll
                 for (int i = 0; i < kChunk; i++) acc[i] = overdrive_generic(acc[i], B[i], D[i], L[i]);
             } else {
@@ -482,10 +487,10 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
         } break;
         case OP_MIX: {
             float b[kChunk];
-            load16(c.vregs + (op.vreg * 4) * kThreads + t, kThreads, b);
+            load16(c.vregs + (op.vreg * kF4) * kThreads + t, kThreads, b);
             if (op.pflags & 1) {
                 float R[kChunk];
-                load16(c.vregs + (op.pv[0] * 4) * kThreads + t, kThreads, R);
+                load16(c.vregs + (op.pv[0] * kF4) * kThreads + t, kThreads, R);
 #pragma unroll
                 for (int i = 0; i < kChunk; i++) acc[i] = add(mul(b[i], R[i]), mul(acc[i], sub(1.0f, R[i])));
             } else {
@@ -499,7 +504,7 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
             const float decay = op.p[0];
             const int pslot = op.aux >> 8;  // 0 = not staged
             float* rrow = r.base + (long long)c.ch * r.D;
-            if ((r.D & 15) == 0 && (r.pos & 15) == 0) {
+            if ((r.D & (kChunk - 1)) == 0 && (r.pos & (kChunk - 1)) == 0) {
                 const long long slot = (r.pos + c.n0) % r.D;
                 float old[kChunk];
 #pragma unroll
@@ -513,7 +518,7 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
                 } else if (c.active) {
                     const float4* p = reinterpret_cast<const float4*>(rrow + slot);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
+                    for (int k = 0; k < kF4; k++) {
                         float4 q = ldg_stream(p + k);
                         old[4 * k] = q.x; old[4 * k + 1] = q.y; old[4 * k + 2] = q.z; old[4 * k + 3] = q.w;
                     }
@@ -523,7 +528,7 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
                     for (int i = 0; i < kChunk; i++) acc[i] = add(acc[i], mul(old[i], decay));
                     float4* p = reinterpret_cast<float4*>(rrow + slot);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) stg_stream(p + k, make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]));
+                    for (int k = 0; k < kF4; k++) stg_stream(p + k, make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]));
                 }
             } else if (c.active) {  // ring length not a multiple of 16: element-wise wrap
                 long long slot = (r.pos + c.n0) % r.D;
@@ -540,12 +545,12 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
             // p[n] = b0*x[n] + b1*x[n-1] + b2*x[n-2] in the reference's order, time-parallel
             const float b0 = op.p[0], b1 = op.p[1], b2 = op.p[2];
             float4* st = c.sm_state + op.aux * G;
-            c.edge[t] = make_float2(acc[14], acc[15]);
+            c.edge[t] = make_float2(acc[kChunk - 2], acc[kChunk - 1]);
             __syncthreads();
             float xm1, xm2;
             if (c.j == 0) { const float4 s = st[c.g]; xm1 = s.x; xm2 = s.y; }
             else { const float2 e = c.edge[t - 1]; xm2 = e.x; xm1 = e.y; }
-            const float nx1 = acc[15], nx2 = acc[14];
+            const float nx1 = acc[kChunk - 1], nx2 = acc[kChunk - 2];
             float pm1 = acc[0], pm2;
             acc[0] = add(add(mul(b0, acc[0]), mul(b1, xm1)), mul(b2, xm2));
             pm2 = pm1; pm1 = acc[1];
@@ -584,7 +589,7 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
         } break;
         case OP_SIGGEN: {  // nodes/signal_gen.rs:55-130: phase accumulates per 128-sample reference block
             float A[kChunk];
-            if (op.pflags & 1) load16(c.vregs + (op.pv[0] * 4) * kThreads + t, kThreads, A);
+            if (op.pflags & 1) load16(c.vregs + (op.pv[0] * kF4) * kThreads + t, kThreads, A);
             else {
 #pragma unroll
                 for (int i = 0; i < kChunk; i++) A[i] = op.p[0];
@@ -596,22 +601,22 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
             }
             using Q = Geo<G>;
             const float sr = op.p[2];
-            const int pos = (c.j & 7) * kChunk;  // first sample of this chunk inside its 128-block
+            const int pos = (c.j & (kBlk - 1)) * kChunk;  // first sample of this chunk inside its 128-block
             float tot[kChunk], total_end;
             if (op.pflags & 2) {  // frequency from a control port: sequential f32 sum of the block's steps
                 __syncthreads();  // the seven other threads of the block wrote their frequency tiles
-                const float4* fv = c.vregs + (op.pv[1] * 4) * kThreads;
+                const float4* fv = c.vregs + (op.pv[1] * kF4) * kThreads;
                 float run = 0.0f;
-                const int t0 = t - (c.j & 7);
-                for (int th = 0; th < 8; th++) {
+                const int t0 = t - (c.j & (kBlk - 1));
+                for (int th = 0; th < kBlk; th++) {
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
+                    for (int k = 0; k < kF4; k++) {
                         const float4 q = fv[k * kThreads + t0 + th];
                         const float f4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
                             run = add(run, dv(f4[e], sr));
-                            if (th == (c.j & 7)) tot[4 * k + e] = run;
+                            if (th == (c.j & (kBlk - 1))) tot[4 * k + e] = run;
                         }
                     }
                 }
@@ -629,11 +634,11 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
             // With a modulated frequency every block has its own total: exchange them through edge[].
             float4* st = c.sm_state + op.aux * G;
             float clk = st[c.g].x;
-            const int blk = c.j >> 3;  // block index inside the tile
+            const int blk = c.j / kBlk;  // block index inside the tile
             __syncthreads();
-            if ((c.j & 7) == 0) c.edge[t >> 3] = make_float2(total_end, 0.0f);
+            if ((c.j & (kBlk - 1)) == 0) c.edge[t / kBlk] = make_float2(total_end, 0.0f);
             __syncthreads();
-            const int blk0 = (c.g * Q::TPC) >> 3;
+            const int blk0 = (c.g * Q::TPC) / kBlk;
             for (int b = 0; b < blk; b++) clk = fmodf(add(clk, c.edge[blk0 + b].x), 1.0f);
             const float TAU = 6.28318530717958647692528676655900577f;
 #pragma unroll
@@ -722,10 +727,10 @@ fused_kernel(const __grid_constant__ Program prog, int c_begin, int c_end, long 
 
     // shared memory carve-up
     c.sm_state = smem4;                                                  // [kMaxStates][G]
-    c.edge = reinterpret_cast<float2*>(c.sm_state + kMaxStates * G);     // [256] chunk-edge samples
+    c.edge = reinterpret_cast<float2*>(c.sm_state + kMaxStates * G);     // [kThreads] chunk-edge samples
     float* tile = reinterpret_cast<float*>(c.edge + kThreads);
-    c.stage = reinterpret_cast<float4*>(tile + (prog.needs_tile ? G * Q::ROW : 0));  // [n_prefetch][4][256]
-    c.vregs = c.stage;                                                               // [n_vregs][4][256]
+    c.stage = reinterpret_cast<float4*>(tile + (prog.needs_tile ? G * Q::ROW : 0));  // (unused: prefetch lives in registers)
+    c.vregs = c.stage;                                                               // [n_vregs][kF4][kThreads]
 
     for (int i = t; i < n_states * G; i += kThreads) {
         int s = i / G, cc = c_begin + blockIdx.x * G + (i % G);
@@ -752,7 +757,7 @@ fused_kernel(const __grid_constant__ Program prog, int c_begin, int c_end, long 
         c.active = c.ch_ok && c.n0 < T;
         const long long rem = T - tile_i * Q::S;
         c.tc.valid_f4 = (int)((rem < Q::S ? rem : Q::S) / 4);
-        c.j_last = c.tc.valid_f4 / 4 - 1;  // thread holding the last valid chunk of each channel
+        c.j_last = c.tc.valid_f4 / kF4 - 1;  // thread holding the last valid chunk of each channel
 
         __syncthreads();  // ring / tile hazards across tiles
 
@@ -936,7 +941,7 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
         c.active = c.ch_ok && c.n0 < T;
         const long long rem = T - ti * Q::S;
         c.tc.valid_f4 = (int)((rem < Q::S ? rem : Q::S) / 4);
-        c.j_last = c.tc.valid_f4 / 4 - 1;
+        c.j_last = c.tc.valid_f4 / kF4 - 1;
     };
 
     for (long long i = 0; i <= n_tiles; i++) {
@@ -972,7 +977,7 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
             if (rpre & 2) div16(acc, ConstDiv{rop.p[4], rop.p[5]}, rpre & 4);
             if (rcode == OP_BIQUAD) {
                 const float b0 = rop.p[0], b1 = rop.p[1], b2 = rop.p[2];
-                edge[t] = make_float2(acc[14], acc[15]);
+                edge[t] = make_float2(acc[kChunk - 2], acc[kChunk - 1]);
                 bar_sync(BAR_EONLY, kThreads);
 #ifdef DSPB_WS_TIMING
                 tp2 = clock64();
@@ -980,7 +985,7 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
                 float xm1, xm2;
                 if (c.j == 0) { const float2 s2 = xstate[c.g]; xm1 = s2.x; xm2 = s2.y; }
                 else { const float2 e = edge[t - 1]; xm2 = e.x; xm1 = e.y; }
-                const float nx1 = acc[15], nx2 = acc[14];
+                const float nx1 = acc[kChunk - 1], nx2 = acc[kChunk - 2];
                 float pm1 = acc[0], pm2;
                 acc[0] = add(add(mul(b0, acc[0]), mul(b1, xm1)), mul(b2, xm2));
                 pm2 = pm1; pm1 = acc[1];
@@ -1003,8 +1008,8 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
             }
             float4* row = reinterpret_cast<float4*>(tiles + (int)(i & 1) * (G * Q::ROW) + c.g * Q::ROW);
 #pragma unroll
-            for (int k = 0; k < 4; k++)
-                row[4 * c.j + (k ^ ((c.j >> 1) & 3))] = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+            for (int k = 0; k < kF4; k++)
+                row[kF4 * c.j + (k ^ sw_of(c.j))] = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
             __threadfence_block();
             bar_arrive(BAR_FULL0 + (int)(i & 1), kWsThreads);
         }
@@ -1020,8 +1025,8 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
             set_tile(i - 1);
             const float4* row = reinterpret_cast<const float4*>(tiles + b * (G * Q::ROW) + c.g * Q::ROW);
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const float4 q = row[4 * c.j + (k ^ ((c.j >> 1) & 3))];
+            for (int k = 0; k < kF4; k++) {
+                const float4 q = row[kF4 * c.j + (k ^ sw_of(c.j))];
                 acc[4 * k] = q.x; acc[4 * k + 1] = q.y; acc[4 * k + 2] = q.z; acc[4 * k + 3] = q.w;
             }
             if constexpr (Chain::n > 0) run_static_range<G, Chain, Chain::rec + 1, Chain::n>(prog, c, acc, pf);

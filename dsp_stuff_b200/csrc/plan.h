@@ -2,8 +2,8 @@
 // (engine.cpp) and the kernels (fused_chain.cu, fir_fft.cu).
 //
 // One fused kernel runs a straight-line program over a tile of [G channels x S samples]
-// (G*S = 4096, 256 threads, 16 consecutive samples of one channel per thread).  The program is an
-// accumulator machine: `acc` is the thread's 16 samples in registers; other live values sit in
+// (G*S = 4096, 512 threads, 8 consecutive samples of one channel per thread).  The program is an
+// accumulator machine: `acc` is the thread's 8 samples in registers; other live values sit in
 // thread-private shared-memory "vregs" or in global scratch.  Recurrences (biquad, one-pole,
 // envelope) run lane = channel, strictly sequential in time, so they are bit-identical to the
 // reference arithmetic (DESIGN.md "IIR exactness").
@@ -14,8 +14,8 @@
 
 namespace dspb {
 
-constexpr int kThreads = 256;       // threads per CTA
-constexpr int kChunk = 16;          // consecutive samples per thread
+constexpr int kThreads = 512;       // elementwise threads per CTA
+constexpr int kChunk = 8;           // consecutive samples per thread (8: twice the warps of 16 for latency hiding)
 constexpr int kTile = kThreads * kChunk;  // 4096 samples per CTA tile
 constexpr int kRefBlock = 128;      // node.rs:257 BUF_SIZE
 constexpr int kMaxOps = 48;
