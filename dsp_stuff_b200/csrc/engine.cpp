@@ -542,6 +542,13 @@ void Lowerer::close_fused() {
             P.n_prefetch++;
             break;
         }
+    P.st_buf = -1;
+    for (int i = 0; i < P.n_ops; i++)
+        if (P.ops[i].code == OP_STOREG) {
+            P.st_buf = P.ops[i].buf;
+            P.ops[i].aux = 1;
+            break;
+        }
     static const bool ring_prefetch = !(getenv("DSPB_RING_PREFETCH") && atoi(getenv("DSPB_RING_PREFETCH")) == 0);
     for (int i = 0; i < P.n_ops && ring_prefetch; i++)
         if (P.ops[i].code == OP_COMB) {

@@ -240,33 +240,52 @@ struct Ctx {
     float4* stage;
     float4* vregs;
     TileCtx tc;
-    long long n0, tile_i, n_tiles, T;
+    int n0, tile_i, n_tiles, T;  // samples per call < 2^31 (checked by the launcher)
     int t, g, j, ch, j_last;
     bool ch_ok, active;
+    // Loop-carried addressing of the three streams every tile touches (prefetched input, prefetched ring,
+    // first stored output): row pointers are computed once per thread, the ring slot advances by S with a
+    // compare-and-subtract.  Recomputing them from the tile index cost ~150 of the ~800 instructions a thread
+    // spent per tile (64-bit multiplies and two 32-bit modulo sequences).
+    const float* in_row;
+    float* out_row;
+    float* ring_row;
+    int ring_D;
+    mutable int ring_slot;  // this thread's ring slot of the tile whose comb runs next
+
+    template <class P>
+    __device__ __forceinline__ void init_streams(const P& pr) {
+        in_row = nullptr; out_row = nullptr; ring_row = nullptr; ring_D = 1; ring_slot = 0;
+        if (pr.pf_buf[0] >= 0) { const BufDesc& b = pr.bufs[pr.pf_buf[0]]; in_row = b.base + (long long)ch * b.row_stride; }
+        if (pr.st_buf >= 0) { const BufDesc& b = pr.bufs[pr.st_buf]; out_row = b.base + (long long)ch * b.row_stride; }
+        if (pr.pf_ring[1] >= 0) {
+            const RingDesc& r = pr.rings[pr.pf_ring[1]];
+            ring_row = r.base + (long long)ch * r.D;
+            ring_D = (int)r.D;
+            ring_slot = (int)((r.pos + (long long)j * kChunk) % r.D);
+        }
+    }
 
     // Register prefetch, one tile ahead: right after a tile's input chunk (slot 0: the first streamed global
     // read) or ring chunk (slot 1: the first eligible comb ring) has been copied out of pf_*, the loads for
     // the next tile are issued straight into the same registers and stay in flight while this tile computes.
     // (An earlier version staged these through shared memory with cp.async; its 16 extra shared-memory
     // instructions per thread and tile clogged the SM-wide LSU queue the sequential R warp depends on.)
-    __device__ __forceinline__ const float* prefetch_src(int s, long long ti, bool& ok) const {
-        using Q = Geo<G>;
-        const long long m0 = ti * Q::S + (long long)j * kChunk;
-        ok = ch_ok && ti < n_tiles && m0 < T;
-        if (s == 0) {
-            const BufDesc& b = prog->bufs[prog->pf_buf[0]];
-            return b.base + (long long)ch * b.row_stride + m0;
-        }
-        const RingDesc& r = prog->rings[prog->pf_ring[1]];
-        return r.base + (long long)ch * r.D + (r.pos + m0) % r.D;
-    }
     // The destination must be a register array of the kernel itself (like `acc`), NOT a member of this struct:
     // the struct lives in local memory inside the interpreter loop, and a load whose result is stored to the
     // stack right away stalls on it immediately (measured: the "prefetch" then hides nothing).
-    __device__ __forceinline__ void prefetch(int slot, long long ti, float (&pf)[kChunk]) const {
-        bool ok;
-        const float4* p = reinterpret_cast<const float4*>(prefetch_src(slot, ti, ok));
-        if (ok) {
+    __device__ __forceinline__ void prefetch_in(int ti, float (&pf)[kChunk]) const {
+        const int m0 = ti * Geo<G>::S + j * kChunk;
+        if (ch_ok && m0 < T) {
+            const float4* p = reinterpret_cast<const float4*>(in_row + m0);
+#pragma unroll
+            for (int k = 0; k < kF4; k++) ldg_prefetch(p + k, pf[4 * k], pf[4 * k + 1], pf[4 * k + 2], pf[4 * k + 3]);
+        }
+    }
+    // ring chunk at `slot` for the tile whose first sample (of this thread) is m0
+    __device__ __forceinline__ void prefetch_ring(int slot, int m0, float (&pf)[kChunk]) const {
+        if (ch_ok && m0 < T) {
+            const float4* p = reinterpret_cast<const float4*>(ring_row + slot);
 #pragma unroll
             for (int k = 0; k < kF4; k++) ldg_prefetch(p + k, pf[4 * k], pf[4 * k + 1], pf[4 * k + 2], pf[4 * k + 3]);
         }
@@ -283,8 +302,8 @@ struct Pf {
 // the generic interpreter.  pre & 1: acc = 0.0 + acc (first link of a fan-in sum, node.rs:181-183);
 // pre & 2: acc /= nf (node.rs:189-191) with the divisor in p[4], its reciprocal in p[5].
 template <int G>
-__device__ __forceinline__ void exec_op(const int code, const int mode, const int pre, const Op& op, const Ctx<G>& c,
-                                        float (&acc)[kChunk], Pf& pf) {
+__device__ __forceinline__ void exec_op(const int code, const int mode, const int pre, const int pfc, const Op& op,
+                                        const Ctx<G>& c, float (&acc)[kChunk], Pf& pf) {
     const Program& prog = *c.prog;
     const int t = c.t;
     if (pre & 1) {
@@ -304,12 +323,17 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
             float v[kChunk];
 #pragma unroll
             for (int i = 0; i < kChunk; i++) v[i] = 0.0f;
-            if (op.aux) {  // prefetched into registers one tile ago; request the next tile right away
+            // pfc: is this op's operand register-prefetched?  0/1 = compile-time (specialised chains), -1 = look
+            // at the op.  It has to be a compile-time fact where speed matters: with both variants in one
+            // kernel ptxas gives the direct load and the prefetch load the same scoreboard, and the first use
+            // of the direct load's registers then waits for the prefetch just issued (ncu: 2 x 11% of all
+            // stall samples on that one instruction).
+            if (pfc < 0 ? op.aux != 0 : pfc != 0) {  // prefetched one tile ago; request the next tile right away
                 if (c.active) {
 #pragma unroll
                     for (int i = 0; i < kChunk; i++) v[i] = pf.in[i];
                 }
-                c.prefetch(0, c.tile_i + 1, pf.in);
+                c.prefetch_in(c.tile_i + 1, pf.in);
             } else if (c.active) {
                 const BufDesc& b = prog.bufs[op.buf];
                 const float4* p = reinterpret_cast<const float4*>(b.base + (long long)c.ch * b.row_stride + c.n0);
@@ -338,8 +362,13 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
         } break;
         case OP_STOREG: {
             if (c.active) {
-                const BufDesc& b = prog.bufs[op.buf];
-                float4* p = reinterpret_cast<float4*>(b.base + (long long)c.ch * b.row_stride + c.n0);
+                float4* p;
+                if (pfc < 0 ? op.aux != 0 : pfc != 0) {
+                    p = reinterpret_cast<float4*>(c.out_row + c.n0);
+                } else {
+                    const BufDesc& b = prog.bufs[op.buf];
+                    p = reinterpret_cast<float4*>(b.base + (long long)c.ch * b.row_stride + c.n0);
+                }
 #pragma unroll
                 for (int k = 0; k < kF4; k++) stg_stream(p + k, make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]));
             }
@@ -504,18 +533,27 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
             const float decay = op.p[0];
             const int pslot = op.aux >> 8;  // 0 = not staged
             float* rrow = r.base + (long long)c.ch * r.D;
-            if ((r.D & (kChunk - 1)) == 0 && (r.pos & (kChunk - 1)) == 0) {
-                const long long slot = (r.pos + c.n0) % r.D;
+            const bool pfd = pfc < 0 ? pslot != 0 : pfc != 0;
+            if (pfd || ((r.D & (kChunk - 1)) == 0 && (r.pos & (kChunk - 1)) == 0)) {
+                long long slot;
                 float old[kChunk];
 #pragma unroll
                 for (int i = 0; i < kChunk; i++) old[i] = 0.0f;
-                if (pslot) {
+                if (pfd) {
                     if (c.active) {
 #pragma unroll
                         for (int i = 0; i < kChunk; i++) old[i] = pf.ring[i];
                     }
-                    c.prefetch(1, c.tile_i + 1, pf.ring);
-                } else if (c.active) {
+                    slot = c.ring_slot;
+                    int nxt = c.ring_slot + Geo<G>::S;
+                    if (nxt >= c.ring_D) nxt -= c.ring_D;
+                    c.ring_slot = nxt;
+                    rrow = c.ring_row;
+                    c.prefetch_ring(nxt, c.n0 + Geo<G>::S, pf.ring);
+                } else {
+                    slot = (r.pos + c.n0) % r.D;
+                }
+                if (!pfd && c.active) {
                     const float4* p = reinterpret_cast<const float4*>(rrow + slot);
 #pragma unroll
                     for (int k = 0; k < kF4; k++) {
@@ -663,41 +701,53 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
 
 // Compile-time op signatures of the BASELINE chains: same exec_op code, opcodes constant-folded.
 // sig(i) packs code | mode << 8 | pre << 16; n = 0 selects the run-time interpreter.
-struct ChainDynamic { static constexpr int n = 0; static constexpr int rec = 0; __host__ __device__ static constexpr int sig(int) { return 0; } };
+struct ChainDynamic { static constexpr int n = 0; static constexpr int rec = 0; __host__ __device__ static constexpr int sig(int) { return 0; } __host__ __device__ static constexpr int pf_of(int) { return -1; } };
 #define DSPB_SIG(code, mode, pre) ((code) | ((mode) << 8) | ((pre) << 16))
+// PF (template argument of the chains): bit 0 = the input chunk (op 0) is register-prefetched, bit 1 = the
+// comb ring chunk is; pf_of(i) is the compile-time pfc of op i.
+template <int PF>
 struct ChainGDBR {  // src -> gain -> distort(SoftClip) -> biquad -> reverb -> store   (config 3 / target front end)
     static constexpr int n = 6;
     static constexpr int rec = 3;
+    __host__ __device__ static constexpr int pf_of(int i) { return i == 0 ? (PF & 1) : i == 4 ? ((PF >> 1) & 1) : i == n - 1 ? 1 : 0; }
     __host__ __device__ static constexpr int sig(int i) {
         return i == 0 ? DSPB_SIG(OP_LOADG, 0, 0) : i == 1 ? DSPB_SIG(OP_GAIN, 0, 6) : i == 2 ? DSPB_SIG(OP_DISTORT, SoftClip, 7)
              : i == 3 ? DSPB_SIG(OP_BIQUAD, 0, 7) : i == 4 ? DSPB_SIG(OP_COMB, 0, 7) : DSPB_SIG(OP_STOREG, 0, 7);
     }
 };
+template <int PF>
 struct ChainGDR {  // src -> gain -> distort(SoftClip) -> reverb -> store   (config 1)
     static constexpr int n = 5;
     static constexpr int rec = -1;
+    __host__ __device__ static constexpr int pf_of(int i) { return i == 0 ? (PF & 1) : i == 3 ? ((PF >> 1) & 1) : i == n - 1 ? 1 : 0; }
     __host__ __device__ static constexpr int sig(int i) {
         return i == 0 ? DSPB_SIG(OP_LOADG, 0, 0) : i == 1 ? DSPB_SIG(OP_GAIN, 0, 6) : i == 2 ? DSPB_SIG(OP_DISTORT, SoftClip, 7)
              : i == 3 ? DSPB_SIG(OP_COMB, 0, 7) : DSPB_SIG(OP_STOREG, 0, 7);
     }
 };
+template <int PF>
 struct ChainBB {  // src -> biquad -> biquad -> store   (config 2)
     static constexpr int n = 4;
     static constexpr int rec = -1;
+    __host__ __device__ static constexpr int pf_of(int i) { return i == 0 ? (PF & 1) : i == -1 ? ((PF >> 1) & 1) : i == n - 1 ? 1 : 0; }
     __host__ __device__ static constexpr int sig(int i) {
         return i == 0 ? DSPB_SIG(OP_LOADG, 0, 0) : i == 1 ? DSPB_SIG(OP_BIQUAD, 0, 6) : i == 2 ? DSPB_SIG(OP_BIQUAD, 0, 7) : DSPB_SIG(OP_STOREG, 0, 7);
     }
 };
+template <int PF>
 struct ChainLH {  // src -> low_pass -> high_pass -> store   (config 2, one-pole variant)
     static constexpr int n = 4;
     static constexpr int rec = -1;
+    __host__ __device__ static constexpr int pf_of(int i) { return i == 0 ? (PF & 1) : i == -1 ? ((PF >> 1) & 1) : i == n - 1 ? 1 : 0; }
     __host__ __device__ static constexpr int sig(int i) {
         return i == 0 ? DSPB_SIG(OP_LOADG, 0, 0) : i == 1 ? DSPB_SIG(OP_LP1, 0, 6) : i == 2 ? DSPB_SIG(OP_HP1, 0, 7) : DSPB_SIG(OP_STOREG, 0, 7);
     }
 };
+template <int PF>
 struct ChainCopy {  // G -> (/nf) -> store   (the segment after a Fir node)
     static constexpr int n = 2;
     static constexpr int rec = -1;
+    __host__ __device__ static constexpr int pf_of(int i) { return i == 0 ? (PF & 1) : i == -1 ? ((PF >> 1) & 1) : i == n - 1 ? 1 : 0; }
     __host__ __device__ static constexpr int sig(int i) { return i == 0 ? DSPB_SIG(OP_LOADG, 0, 0) : DSPB_SIG(OP_STOREG, 0, 6); }
 };
 
@@ -705,7 +755,7 @@ template <int G, class Chain, int I>
 __device__ __forceinline__ void run_static(const Program& prog, const Ctx<G>& c, float (&acc)[kChunk], Pf& pf) {
     if constexpr (I < Chain::n) {
         constexpr int s = Chain::sig(I);
-        exec_op<G>(s & 0xff, (s >> 8) & 0xff, (s >> 16) & 0xff, prog.ops[I], c, acc, pf);
+        exec_op<G>(s & 0xff, (s >> 8) & 0xff, (s >> 16) & 0xff, Chain::pf_of(I), prog.ops[I], c, acc, pf);
         run_static<G, Chain, I + 1>(prog, c, acc, pf);
     }
 }
@@ -722,7 +772,8 @@ fused_kernel(const __grid_constant__ Program prog, int c_begin, int c_end, long 
     c.j = c.t % Q::TPC;
     c.ch = c_begin + blockIdx.x * G + c.g;
     c.ch_ok = c.ch < c_end;
-    c.T = T;
+    c.T = (int)T;
+    c.init_streams(prog);
     const int t = c.t;
 
     // shared memory carve-up
@@ -737,7 +788,7 @@ fused_kernel(const __grid_constant__ Program prog, int c_begin, int c_end, long 
         c.sm_state[s * G + (i % G)] = cc < c_end ? reinterpret_cast<const float4*>(prog.states[s])[cc] : make_float4(0, 0, 0, 0);
     }
 
-    c.n_tiles = (T + Q::S - 1) / Q::S;
+    c.n_tiles = (int)((T + Q::S - 1) / Q::S);
     c.tc.tile = tile;
     c.tc.g = c.g;
     c.tc.j = c.j;
@@ -747,16 +798,16 @@ fused_kernel(const __grid_constant__ Program prog, int c_begin, int c_end, long 
     Pf pf;
 #pragma unroll
     for (int i = 0; i < kChunk; i++) pf.in[i] = pf.ring[i] = 0.0f;
-    if (prog.pf_buf[0] >= 0) c.prefetch(0, 0, pf.in);
-    if (prog.pf_ring[1] >= 0) c.prefetch(1, 0, pf.ring);
+    if (prog.pf_buf[0] >= 0) c.prefetch_in(0, pf.in);
+    if (prog.pf_ring[1] >= 0) c.prefetch_ring(c.ring_slot, c.j * kChunk, pf.ring);
     __syncthreads();
 
-    for (long long tile_i = 0; tile_i < c.n_tiles; tile_i++) {
+    for (int tile_i = 0; tile_i < c.n_tiles; tile_i++) {
         c.tile_i = tile_i;
-        c.n0 = tile_i * Q::S + (long long)c.j * kChunk;
-        c.active = c.ch_ok && c.n0 < T;
-        const long long rem = T - tile_i * Q::S;
-        c.tc.valid_f4 = (int)((rem < Q::S ? rem : Q::S) / 4);
+        c.n0 = tile_i * Q::S + c.j * kChunk;
+        c.active = c.ch_ok && c.n0 < c.T;
+        const int rem = c.T - tile_i * Q::S;
+        c.tc.valid_f4 = (rem < Q::S ? rem : Q::S) / 4;
         c.j_last = c.tc.valid_f4 / kF4 - 1;  // thread holding the last valid chunk of each channel
 
         __syncthreads();  // ring / tile hazards across tiles
@@ -770,7 +821,7 @@ fused_kernel(const __grid_constant__ Program prog, int c_begin, int c_end, long 
         } else {
             for (int ip = 0; ip < prog.n_ops; ip++) {
                 const Op& op = prog.ops[ip];
-                exec_op<G>(op.code, op.mode, op.pre, op, c, acc, pf);
+                exec_op<G>(op.code, op.mode, op.pre, -1, op, c, acc, pf);
             }
         }
     }
@@ -836,7 +887,7 @@ template <int G, class Chain, int I, int END>
 __device__ __forceinline__ void run_static_range(const Program& prog, const Ctx<G>& c, float (&acc)[kChunk], Pf& pf) {
     if constexpr (I < END) {
         constexpr int s = Chain::sig(I);
-        exec_op<G>(s & 0xff, (s >> 8) & 0xff, (s >> 16) & 0xff, prog.ops[I], c, acc, pf);
+        exec_op<G>(s & 0xff, (s >> 8) & 0xff, (s >> 16) & 0xff, Chain::pf_of(I), prog.ops[I], c, acc, pf);
         run_static_range<G, Chain, I + 1, END>(prog, c, acc, pf);
     }
 }
@@ -849,7 +900,7 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
     const int t = threadIdx.x;  // t < kThreads: elementwise thread, else R-warp thread
     // shared memory: [G] x-state (float2) | edge[256] | tiles[2][G*ROW] | stage
     float2* xstate = reinterpret_cast<float2*>(smem4);
-    float2* edge = xstate + 32;
+    float2* edge = xstate + 64;  // xstate[2][32]: read parity i & 1, written parity (i + 1) & 1
     float* tiles = reinterpret_cast<float*>(edge + kThreads);
     float4* stage = reinterpret_cast<float4*>(tiles + 2 * G * Q::ROW);
     const long long n_tiles = (T + Q::S - 1) / Q::S;
@@ -914,12 +965,13 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
     c.j = t % Q::TPC;
     c.ch = c_begin + blockIdx.x * G + c.g;
     c.ch_ok = c.ch < c_end;
-    c.T = T;
+    c.T = (int)T;
+    c.init_streams(prog);
     c.sm_state = nullptr;
     c.edge = edge;
     c.stage = stage;
     c.vregs = nullptr;
-    c.n_tiles = n_tiles;
+    c.n_tiles = (int)n_tiles;
     c.tc.tile = tiles;
     c.tc.g = c.g;
     c.tc.j = c.j;
@@ -931,25 +983,28 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
     Pf pf;
 #pragma unroll
     for (int i = 0; i < kChunk; i++) pf.in[i] = pf.ring[i] = 0.0f;
-    if (prog.pf_buf[0] >= 0) c.prefetch(0, 0, pf.in);
-    if (prog.pf_ring[1] >= 0) c.prefetch(1, 0, pf.ring);
+    if (prog.pf_buf[0] >= 0) c.prefetch_in(0, pf.in);
+    if (prog.pf_ring[1] >= 0) c.prefetch_ring(c.ring_slot, c.j * kChunk, pf.ring);
     bar_sync(BAR_EONLY, kThreads);
 
-    auto set_tile = [&](long long ti) {
+    auto set_tile = [&](int ti) {
         c.tile_i = ti;
-        c.n0 = ti * Q::S + (long long)c.j * kChunk;
-        c.active = c.ch_ok && c.n0 < T;
-        const long long rem = T - ti * Q::S;
-        c.tc.valid_f4 = (int)((rem < Q::S ? rem : Q::S) / 4);
+        c.n0 = ti * Q::S + c.j * kChunk;
+        c.active = c.ch_ok && c.n0 < c.T;
+        const int rem = c.T - ti * Q::S;
+        c.tc.valid_f4 = (rem < Q::S ? rem : Q::S) / 4;
         c.j_last = c.tc.valid_f4 / kF4 - 1;
     };
 
-    for (long long i = 0; i <= n_tiles; i++) {
+    const int nt = (int)n_tiles;
+    for (int i = 0; i <= nt; i++) {
 #ifdef DSPB_WS_TIMING
         long long tb0 = clock64();
         long long tp1 = 0, tp2 = 0;
 #endif
-        bar_sync(BAR_EONLY, kThreads);  // ring hazards across tiles, edge[] reuse
+        // edge[] is rewritten below: from i = 2 on, the BAR_DONE sync of the previous iteration already orders
+        // that behind every thread's reads (and the ring stores of tile i-2 before the loads of tile i-1)
+        if (i <= 1) bar_sync(BAR_EONLY, kThreads);
 #ifdef DSPB_WS_TIMING
         if (blockIdx.x == 0 && t == 0) g_ws_timing[5] += clock64() - tb0;
 #endif
@@ -958,13 +1013,13 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
 #ifdef DSPB_WS_TIMING
         long long te0 = clock64(), te1 = te0, te2 = te0;
 #endif
-        if (i < n_tiles) {  // ---- ops before the recurrence, tile i ----
+        if (i < nt) {  // ---- ops before the recurrence, tile i ----
             set_tile(i);
 #pragma unroll
             for (int k = 0; k < kChunk; k++) acc[k] = 0.0f;
             if constexpr (Chain::n > 0) run_static_range<G, Chain, 0, Chain::rec>(prog, c, acc, pf);
             else
-                for (int ip = 0; ip < rec_index; ip++) exec_op<G>(prog.ops[ip].code, prog.ops[ip].mode, prog.ops[ip].pre, prog.ops[ip], c, acc, pf);
+                for (int ip = 0; ip < rec_index; ip++) exec_op<G>(prog.ops[ip].code, prog.ops[ip].mode, prog.ops[ip].pre, -1, prog.ops[ip], c, acc, pf);
 #ifdef DSPB_WS_TIMING
             tp1 = clock64();
 #endif
@@ -983,7 +1038,7 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
                 tp2 = clock64();
 #endif
                 float xm1, xm2;
-                if (c.j == 0) { const float2 s2 = xstate[c.g]; xm1 = s2.x; xm2 = s2.y; }
+                if (c.j == 0) { const float2 s2 = xstate[(i & 1) * 32 + c.g]; xm1 = s2.x; xm2 = s2.y; }
                 else { const float2 e = edge[t - 1]; xm2 = e.x; xm1 = e.y; }
                 const float nx1 = acc[kChunk - 1], nx2 = acc[kChunk - 2];
                 float pm1 = acc[0], pm2;
@@ -996,8 +1051,7 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
                     acc[k] = add(add(mul(b0, xi), mul(b1, pm1)), mul(b2, pm2));
                     pm2 = pm1; pm1 = xi;
                 }
-                bar_sync(BAR_EONLY, kThreads);  // every thread has read xstate before it is replaced
-                if (c.j == c.j_last) xstate[c.g] = make_float2(nx1, nx2);
+                if (c.j == c.j_last) xstate[((i + 1) & 1) * 32 + c.g] = make_float2(nx1, nx2);
             } else if (rcode == OP_LP1) {
                 const float omr = rop.p[1];
 #pragma unroll
@@ -1031,7 +1085,7 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
             }
             if constexpr (Chain::n > 0) run_static_range<G, Chain, Chain::rec + 1, Chain::n>(prog, c, acc, pf);
             else
-                for (int ip = rec_index + 1; ip < prog.n_ops; ip++) exec_op<G>(prog.ops[ip].code, prog.ops[ip].mode, prog.ops[ip].pre, prog.ops[ip], c, acc, pf);
+                for (int ip = rec_index + 1; ip < prog.n_ops; ip++) exec_op<G>(prog.ops[ip].code, prog.ops[ip].mode, prog.ops[ip].pre, -1, prog.ops[ip], c, acc, pf);
         }
 #ifdef DSPB_WS_TIMING
         if (blockIdx.x == 0 && t == 0) { long long te3 = clock64(); g_ws_timing[2] += te1 - te0; g_ws_timing[3] += te2 - te1; g_ws_timing[4] += te3 - te2;
@@ -1041,7 +1095,7 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
     bar_sync(BAR_EONLY, kThreads);
     if (rcode == OP_BIQUAD && t < G) {
         const int ch = c_begin + blockIdx.x * G + t;
-        if (ch < c_end) *reinterpret_cast<float2*>(stp + 4 * (long long)ch) = xstate[t];
+        if (ch < c_end) *reinterpret_cast<float2*>(stp + 4 * (long long)ch) = xstate[(nt & 1) * 32 + t];
     }
 }
 
@@ -1058,7 +1112,7 @@ namespace {
 int ws_smem_bytes(const Program& prog, int G) {
     const int S = kTile / G;
     (void)prog;
-    return 32 * 8 + kThreads * 8 + 2 * G * (S + 4) * 4;
+    return 64 * 8 + kThreads * 8 + 2 * G * (S + 4) * 4;
 }
 // index of the single recurrence op if the program qualifies for the warp-specialised kernel, else -1
 int ws_rec_index(const Program& p) {
@@ -1097,6 +1151,9 @@ bool chain_matches(const Program& p) {
         const Op& o = p.ops[i];
         if (o.code != (s & 0xff) || o.pre != ((s >> 16) & 0xff) || o.pflags != 0) return false;
         if (o.code == OP_DISTORT && o.mode != ((s >> 8) & 0xff)) return false;
+        const bool is_src = o.code == OP_LOADG || o.code == OP_ADDG || o.code == OP_COPYG || o.code == OP_STOREG;
+        const int has = is_src ? (o.aux != 0) : o.code == OP_COMB ? ((o.aux >> 8) != 0) : 0;
+        if (has != Chain::pf_of(i)) return false;
     }
     return true;
 }
@@ -1128,15 +1185,17 @@ int launch_g(const Program& prog, int c_begin, int c_end, int64_t T, int n_state
     static const bool no_ws = getenv("DSPB_NO_WS") != nullptr;
     const int rec = (G <= 32 && !no_ws) ? ws_rec_index(prog) : -1;
     if (rec >= 0 && ws_smem_bytes(prog, G) <= 200 * 1024) {
-        if (!no_static && chain_matches<ChainGDBR>(prog)) return launch_ws<G, ChainGDBR>(prog, c_begin, c_end, T, rec, st);
+        if (!no_static && chain_matches<ChainGDBR<3>>(prog)) return launch_ws<G, ChainGDBR<3>>(prog, c_begin, c_end, T, rec, st);
+        if (!no_static && chain_matches<ChainGDBR<1>>(prog)) return launch_ws<G, ChainGDBR<1>>(prog, c_begin, c_end, T, rec, st);
         return launch_ws<G, ChainDynamic>(prog, c_begin, c_end, T, rec, st);
     }
     if (!no_static) {
-        if (chain_matches<ChainGDBR>(prog)) return launch_gc<G, ChainGDBR>(prog, c_begin, c_end, T, n_states, st);
-        if (chain_matches<ChainGDR>(prog)) return launch_gc<G, ChainGDR>(prog, c_begin, c_end, T, n_states, st);
-        if (chain_matches<ChainBB>(prog)) return launch_gc<G, ChainBB>(prog, c_begin, c_end, T, n_states, st);
-        if (chain_matches<ChainLH>(prog)) return launch_gc<G, ChainLH>(prog, c_begin, c_end, T, n_states, st);
-        if (chain_matches<ChainCopy>(prog)) return launch_gc<G, ChainCopy>(prog, c_begin, c_end, T, n_states, st);
+        if (chain_matches<ChainGDBR<3>>(prog)) return launch_gc<G, ChainGDBR<3>>(prog, c_begin, c_end, T, n_states, st);
+        if (chain_matches<ChainGDR<3>>(prog)) return launch_gc<G, ChainGDR<3>>(prog, c_begin, c_end, T, n_states, st);
+        if (chain_matches<ChainGDR<1>>(prog)) return launch_gc<G, ChainGDR<1>>(prog, c_begin, c_end, T, n_states, st);
+        if (chain_matches<ChainBB<1>>(prog)) return launch_gc<G, ChainBB<1>>(prog, c_begin, c_end, T, n_states, st);
+        if (chain_matches<ChainLH<1>>(prog)) return launch_gc<G, ChainLH<1>>(prog, c_begin, c_end, T, n_states, st);
+        if (chain_matches<ChainCopy<1>>(prog)) return launch_gc<G, ChainCopy<1>>(prog, c_begin, c_end, T, n_states, st);
     }
     return launch_gc<G, ChainDynamic>(prog, c_begin, c_end, T, n_states, st);
 }
@@ -1180,6 +1239,9 @@ int fused_smem_bytes(const Program& prog, int G) {
 
 int launch_fused(const Program& prog, int G, int c_begin, int c_end, int64_t T, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    if (T <= 0 || T > (1ll << 30)) return (int)cudaErrorInvalidValue;  // the kernels index samples of one call with int
+    for (int k = 0; k < kMaxPrefetch; k++)
+        if (prog.pf_ring[k] >= 0 && prog.rings[prog.pf_ring[k]].D > (1ll << 30)) return (int)cudaErrorInvalidValue;
     int n_states = 0;
     for (int i = 0; i < kMaxStates; i++)
         if (prog.states[i]) n_states = i + 1;

@@ -91,6 +91,7 @@ struct Program {
     // prefetch slot k stages global buffer pf_buf[k] (>=0) or ring pf_ring[k] (>=0)
     int16_t pf_buf[kMaxPrefetch];
     int16_t pf_ring[kMaxPrefetch];
+    int16_t st_buf;        // buffer of the first STOREG (its op has aux = 1): row pointer kept in a register, or -1
 };
 
 // ---- launchers (defined in the .cu files) -----------------------------------------------------------
