@@ -289,9 +289,12 @@ fir_fft_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, fl
         const int u = t + kNT * k, base = 16 * u;
         C2<float> v[16];
         float4 h[8];
-        const float4* h4 = reinterpret_cast<const float4*>(H + base);
+        // H is stored [k][s / 2][thread] (float4 = two consecutive bins): every request of a warp is one
+        // contiguous 512-byte run.  (In natural order each thread owns a 128-byte line: 32 lines per request,
+        // which alone kept the L1 data pipe 84 % busy -- ncu l1tex__data_pipe_lsu_wavefronts.)
+        const float4* h4 = reinterpret_cast<const float4*>(H) + (k * 8) * kNT + t;
 #pragma unroll
-        for (int s = 0; s < 8; s++) h[s] = __ldg(h4 + s);
+        for (int s = 0; s < 8; s++) h[s] = __ldg(h4 + s * kNT);
 #pragma unroll
         for (int s = 0; s < 16; s++) v[s] = a[pad(base) + s];
         fft_dif<16>(v);
@@ -371,7 +374,8 @@ fir_spectrum_kernel(const double* __restrict__ taps_rev, int N, const double2* _
         for (int s = 0; s < 16; s++) v[s] = a[pad(base) + s];
         fft_dif<16>(v);
 #pragma unroll
-        for (int s = 0; s < 16; s++) Hout[base + s] = make_float2((float)(v[s].x / kF), (float)(v[s].y / kF));
+        for (int s = 0; s < 16; s++)  // [k][s / 2][thread] float4 order, see fir_fft_kernel
+            Hout[((k * 8 + (s >> 1)) * kNT + t) * 2 + (s & 1)] = make_float2((float)(v[s].x / kF), (float)(v[s].y / kF));
     }
 }
 
