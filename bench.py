@@ -50,7 +50,11 @@ def parse_args():
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
 # `ncu --set full` captures (profiles/): keyed by (workload, kernel kind); None = not captured yet.
-TRAFFIC = {}
+# (workload, kind, channels, samples per step) -> bytes
+TRAFFIC = {
+    ("target", "fir", 4096, 16384): 335779840 + 229628672,     # profiles/r01s3_target_fir_fft_kernel.txt
+    ("target", "fused", 4096, 16384): 539016192 + 484716032,   # profiles/r01s3_target_fused_chain_kernel.txt
+}
 
 DEFAULT_CHANNELS = {"config1": 2, "config2": 256, "config3": 1024, "config4": 4096, "config5": 1024, "target": 4096}
 
@@ -305,7 +309,7 @@ def main():
                        "l2_policy": f"inputs+outputs {2 * C * n * 4 / 2**20:.0f} MiB per step exceed the 126 MB L2",
                        "x_realtime_per_channel": value / world / C / 48000.0},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": TRAFFIC.get((args.workload, dom["kind"])), "peak_source": peak_src,
+                         "traffic": TRAFFIC.get((args.workload, dom["kind"], C, n)), "peak_source": peak_src,
                          "kernel": f"step {dom['step']} ({dom['kind']})", "kernel_avg_ms": dom["avg_ms"],
                          "kernel_alg_bytes_per_channel_sample": dom["alg_bytes_per_channel_sample"],
                          "kernel_share_of_step": dom["share_of_step"], "kernels": kernels,
