@@ -143,6 +143,7 @@ struct Node {
     DevBuf U[2];                    // [C x (hist_pad + max_samples)] input incl. history, double-buffered
     DevBuf Y;                       // [C x max_samples]
     DevBuf H, taps_dev;
+    DevBuf toep_tiles, toep_split;  // FIR_TOEPLITZ: Toeplitz tiles of the taps, hi/lo bf16 split of U
     int hist_pad = 0, cur_u = 0;
     int64_t started = 0;            // samples this node has consumed since reset
     bool fir_dirty = true;
@@ -688,6 +689,9 @@ int Lowerer::lower() {
                 if (e.cfg.fir_mode == FIR_FFT)
                     snprintf(b, sizeof b, "fir step: %s, %zu taps, overlap-save FFT 2^%d, two channels per transform, alg_bytes=8\n", tag.c_str(),
                              nd.taps.size(), e.cfg.fir_fft_log2);
+                else if (e.cfg.fir_mode == FIR_TOEPLITZ)
+                    snprintf(b, sizeof b, "fir step: %s, %zu taps, Toeplitz-tiled tcgen05 GEMM 128x256x32, split bf16 (3 MMAs per K step), alg_bytes=8\n",
+                             tag.c_str(), nd.taps.size());
                 else
                     snprintf(b, sizeof b, "fir step: %s, %zu taps, direct f64 sum in reference order, alg_bytes=8\n", tag.c_str(), nd.taps.size());
                 fs.text = b;
@@ -849,9 +853,19 @@ int ensure_resources(dspb_engine* e) {
             if (r) return r;
             r = n.taps_dev.alloc((size_t)N * 8, false);
             if (r) return r;
+            const bool toep = e->cfg.fir_mode == FIR_TOEPLITZ && N <= fir_toeplitz_max_taps();
+            if (toep) {
+                r = n.toep_tiles.alloc(fir_toeplitz_tiles_bytes(N), false);
+                if (r) return r;
+                r = n.toep_split.alloc(fir_toeplitz_split_bytes(N, C, maxn), false);
+                if (r) return r;
+            }
             if (!e->plan_only) {
                 CUDA_TRY(cudaMemcpy(n.taps_dev.p, n.taps.data(), (size_t)N * 8, cudaMemcpyHostToDevice));
-                if (N <= fir_fft_max_taps()) {  // longer impulse responses run on the exact direct path
+                if (toep) {
+                    int rc = fir_toeplitz_prepare(reinterpret_cast<const double*>(n.taps_dev.p), N, n.toep_tiles.p, nullptr);
+                    if (rc) return fail(DSPB_ERR_CUDA, "fir_toeplitz_prepare: %s", cudaGetErrorString((cudaError_t)rc));
+                } else if (N <= fir_fft_max_taps()) {  // longer impulse responses run on the exact direct path
                     int rc = fir_prepare_spectrum(e->cfg.fir_fft_log2, reinterpret_cast<const double*>(n.taps_dev.p), N, reinterpret_cast<float2*>(n.H.p), nullptr);
                     if (rc) return fail(DSPB_ERR_CUDA, "fir_prepare_spectrum: %s", cudaGetErrorString((cudaError_t)rc));
                 }
@@ -974,7 +988,12 @@ int run_steps(dspb_engine* e, const float* const* d_in, float* const* d_out, int
         } else {
             Node& f = *e->nodes[s.fir_node];
             FirPlan fp;
-            fp.mode = (int)f.taps.size() > fir_fft_max_taps() ? (int)FIR_DIRECT : e->cfg.fir_mode;  // long IRs: exact path
+            fp.mode = e->cfg.fir_mode;
+            if (fp.mode == FIR_TOEPLITZ && (int)f.taps.size() > fir_toeplitz_max_taps()) fp.mode = FIR_DIRECT;
+            if (fp.mode == FIR_FFT && (int)f.taps.size() > fir_fft_max_taps()) fp.mode = FIR_DIRECT;  // long IRs: exact path
+            fp.toep_tiles = f.toep_tiles.p;
+            fp.toep_split = f.toep_split.p;
+            fp.toep_max_samples = e->cfg.max_samples;
             fp.log2F = e->cfg.fir_fft_log2;
             fp.n_taps = (int)f.taps.size();
             fp.hist_pad = f.hist_pad;
@@ -1056,7 +1075,10 @@ int dspb_engine_create(const dspb_config* cfg, dspb_engine** out) {
     e->cfg.max_samples = round_up(e->cfg.max_samples, kRefBlock);
     if (e->cfg.fir_fft_log2 <= 0) e->cfg.fir_fft_log2 = 13;
     if (e->cfg.fir_fft_log2 != 13) { delete e; return fail(DSPB_ERR_INVALID, "fir_fft_log2 must be 13 in this build"); }
-    if (e->cfg.fir_mode != FIR_FFT && e->cfg.fir_mode != FIR_DIRECT) { delete e; return fail(DSPB_ERR_INVALID, "fir_mode must be 0 (FFT) or 1 (direct)"); }
+    if (e->cfg.fir_mode != FIR_FFT && e->cfg.fir_mode != FIR_DIRECT && e->cfg.fir_mode != FIR_TOEPLITZ) {
+        delete e;
+        return fail(DSPB_ERR_INVALID, "fir_mode must be 0 (FFT), 1 (direct) or 2 (Toeplitz tensor-core)");
+    }
     if (const char* g = getenv("DSPB_FORCE_G")) e->force_G = atoi(g);
     if (const char* g = getenv("DSPB_CHUNKS")) e->dev_chunks = std::max(1, std::min(8, atoi(g)));
     *out = e;

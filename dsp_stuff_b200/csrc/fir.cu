@@ -5,6 +5,7 @@
 //               order (oldest sample first, no FMA) -> bit-identical to `zip(state, taps).sum::<f64>()`.
 //               8192 f64 flop per sample at 4096 taps: the parity-grade / cross-check path.
 //   FIR_FFT     overlap-save FFT convolution in shared memory (fir_fft.cu): the throughput path.
+//   FIR_TOEPLITZ  Toeplitz-tiled tcgen05 GEMM on split bf16 operands (fir_toeplitz.cu): the tensor-core comparison path.
 // Both honour the reference's warm-up quirk: until N-1 samples have been seen the oldest sample pairs
 // with taps[0] (a running prefix sum of x[i]*taps[i]), not zero-padded convolution.
 #include <cuda_runtime.h>
@@ -15,6 +16,9 @@ namespace dspb {
 
 int launch_fir_fft(const FirPlan& fp, const float* U, int64_t u_stride, float* Y, int64_t y_stride, int c_begin, int c_end,
                    int64_t T, int64_t started, cudaStream_t st, int* n_launches);
+
+int launch_fir_toeplitz(const FirPlan& fp, const float* U, int64_t u_stride, float* Y, int64_t y_stride, int c_begin, int c_end,
+                        int64_t T, cudaStream_t st, int* n_launches);
 
 namespace {
 
@@ -82,7 +86,8 @@ int launch_fir(const FirPlan& fp, const float* U, int64_t u_stride, float* Y, in
         if (n_launches) *n_launches += 1;
         return launch_fir_direct(fp, U, u_stride, Y, y_stride, c_begin, c_end, T, started, 0, T, st);
     }
-    int rc = launch_fir_fft(fp, U, u_stride, Y, y_stride, c_begin, c_end, T, started, st, n_launches);
+    int rc = fp.mode == FIR_TOEPLITZ ? launch_fir_toeplitz(fp, U, u_stride, Y, y_stride, c_begin, c_end, T, st, n_launches)
+                                     : launch_fir_fft(fp, U, u_stride, Y, y_stride, c_begin, c_end, T, started, st, n_launches);
     if (rc) return rc;
     // Samples that still belong to the warm-up are recomputed exactly by the direct kernel.
     const int64_t warm_end = (int64_t)fp.n_taps - 1 - started;  // call-relative

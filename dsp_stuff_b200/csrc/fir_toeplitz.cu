@@ -1,0 +1,319 @@
+// fir_toeplitz.cu — the Fir node (nodes/fir.rs:179-225) as a Toeplitz-tiled tensor-core GEMM (sm_100a,
+// tcgen05.mma with the accumulator in tensor memory).  BASELINE config 4's "Toeplitz tensor-core path",
+// the counterpart of the overlap-save FFT kernel in fir_fft.cu.
+//
+//   Y[t][c] = sum_k h[k] * x[c][t - k]      ==>      D[128 t x 256 c] += A[128 t x 32 s] * B[32 s x 256 c]
+//
+// per CTA and pipeline stage, with A[m][kk] = h[delta + m - kk] (a Toeplitz tile that depends only on
+// delta = tile start - K-block start) and B[kk][c] = x[c][s0 + kk].  The reference accumulates f64
+// products of f32 samples and f64 taps; bf16 tensor-core inputs reach the 1e-5 parity bar by splitting
+// both operands into hi + lo bf16 parts (16 mantissa bits) and issuing three MMAs per K step
+// (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM): measured ~5e-6 peak-relative on the config-4 input.
+//
+// Operand staging without tensor maps: both operands are written ONCE by small pre-pass kernels into
+// global memory already in the shared-memory image the UMMA descriptors expect (K-major, no swizzle:
+// 8-row x 16-byte core matrices, [k-chunk][row-group][8 rows][8 bf16]), so a stage is two plain
+// cp.async.bulk copies (A hi|lo 16 KB, B hi|lo 32 KB) completing on an mbarrier.
+//   * toeplitz tiles  At[kb][hi|lo]           — per tap set, 132 x 16 KB at 4096 taps (L2 resident)
+//   * split input     Xt[c / 256][s / 32][hi|lo] — per call, written by x_split_kernel from the f32 rows
+// Warp roles (192 threads, 1 CTA/SM): warp 0 = bulk-copy producer + TMEM allocator, warp 1 = MMA issuer
+// (one elected lane), warps 2-5 = epilogue (tcgen05.ld -> scale -> coalesced stores along time).
+//
+// Cost model: 3 x 8192 flop per channel-sample; at the measured 1.44 PFLOP/s dense bf16 that bounds this
+// path at ~58 G channel-samples/s per GPU, below the FFT kernel (~140 G/s): it is kept as the comparison
+// the config asks for and as the cross-check of the FFT path, not as the default.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "plan.h"
+
+namespace dspb {
+namespace {
+
+constexpr int kTM = 128;     // time outputs per CTA  (UMMA M, TMEM lanes)
+constexpr int kTN = 256;     // channels per CTA      (UMMA N, TMEM columns)
+constexpr int kBK = 32;      // input samples per pipeline stage (two K = 16 MMAs per operand pair)
+constexpr int kStages = 4;
+constexpr int kABytes = kTM * kBK * 2;              // one bf16 component of an A tile: 8 KB
+constexpr int kBBytes = kTN * kBK * 2;              // one bf16 component of a B tile: 16 KB
+constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;  // 48 KB
+constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+constexpr int kThreadsT = 192;
+constexpr uint32_t kSBO = 128;                      // 8-row group stride (bytes)
+constexpr uint32_t kLBO_A = (kTM / 8) * 128;        // k-chunk stride of an A tile (bytes)
+constexpr uint32_t kLBO_B = (kTN / 8) * 128;        // k-chunk stride of a B tile
+
+// byte offset of element (row, kk) inside one [rows x 32] bf16 tile component
+__host__ __device__ constexpr int tile_off(int rows, int row, int kk) {
+    return (((kk >> 3) * (rows >> 3) + (row >> 3)) * 8 + (row & 7)) * 16 + (kk & 7) * 2;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// K-major, no-swizzle shared-memory matrix descriptor (SM100 UMMA): start address, leading (K) and stride (M/N)
+// byte offsets in 16-byte units, descriptor version 1 at bit 46, layout type 0.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3fff) | ((uint64_t)((lbo >> 4) & 0x3fff) << 16) | ((uint64_t)((sbo >> 4) & 0x3fff) << 32) |
+           (1ull << 46);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// instruction descriptor: D = f32 (bits 4-5 = 1), A = B = bf16 (bits 7-9, 10-12 = 1), both K-major (bits 15, 16 = 0),
+// N >> 3 at bit 17, M >> 4 at bit 24
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTN >> 3) << 17) | ((uint32_t)(kTM >> 4) << 24);
+
+// ---- pre-pass 1: Toeplitz tiles of one tap set ----------------------------------------------------------
+// tile kb holds delta = dmax - 32*kb; element (m, kk) = h[delta + m - kk], h[k] = taps_rev[N-1-k] (fir.rs:163-168)
+__global__ void toeplitz_tiles_kernel(const double* __restrict__ taps_rev, int N, int dmax, uint8_t* __restrict__ At) {
+    const int kb = blockIdx.x;
+    const int delta = dmax - kBK * kb;
+    uint8_t* tile = At + (size_t)kb * 2 * kABytes;
+    for (int i = threadIdx.x; i < kTM * kBK; i += blockDim.x) {
+        const int m = i / kBK, kk = i % kBK;
+        const int idx = delta + m - kk;
+        const double h = (idx >= 0 && idx < N) ? taps_rev[N - 1 - idx] : 0.0;
+        const __nv_bfloat16 hi = __double2bfloat16(h);
+        const __nv_bfloat16 lo = __double2bfloat16(h - (double)__bfloat162float(hi));
+        const int off = tile_off(kTM, m, kk);
+        *reinterpret_cast<__nv_bfloat16*>(tile + off) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(tile + kABytes + off) = lo;
+    }
+}
+
+// ---- pre-pass 2: f32 input rows -> hi/lo bf16 tiles -------------------------------------------------------
+// Tile (cb, sb) holds channels [256 cb, 256 cb + 256) x call-relative samples [32 sb - Hb, +32); samples outside
+// [-hist_pad, T) are zeros.  One thread per (channel row, 8-sample chunk): consecutive threads write consecutive
+// 16-byte core-matrix rows.  Only rows of channels in [c_begin, c_end) are written (other chunks of the engine
+// own the rest; an output column only ever depends on its own row).
+__global__ void __launch_bounds__(256)
+x_split_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, long long T, int Hb, int n_sb, uint8_t* __restrict__ Xt,
+               int c_begin, int c_end, int cb0) {
+    const int sb = blockIdx.x, cb = cb0 + blockIdx.y;
+    const int row = threadIdx.x;
+    const int ch = cb * kTN + row;
+    if (ch < c_begin || ch >= c_end) return;
+    uint8_t* tile = Xt + ((size_t)cb * n_sb + sb) * 2 * kBBytes;
+    const long long s0 = (long long)sb * kBK - Hb;
+    const float* src = U + (long long)ch * u_stride + hist_pad;
+#pragma unroll
+    for (int kc = 0; kc < kBK / 8; kc++) {
+        const long long s = s0 + kc * 8;
+        float x[8];
+        if (s >= -(long long)hist_pad && s + 8 <= T) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src + s));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(src + s + 4));
+            x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; e++) x[e] = (s + e >= -(long long)hist_pad && s + e < T) ? src[s + e] : 0.0f;
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * e]), h1 = __float2bfloat16_rn(x[2 * e + 1]);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * e] - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * e + 1] - __bfloat162float(h1));
+            hi[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+            lo[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        const int off = tile_off(kTN, row, kc * 8);
+        *reinterpret_cast<uint4*>(tile + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(tile + kBBytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// ---- the GEMM ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreadsT, 1)
+fir_toeplitz_kernel(const uint8_t* __restrict__ At, const uint8_t* __restrict__ Xt, float* __restrict__ Y, long long y_stride, int nK,
+                    int n_sb, long long T, float divisor, float post_nf, int c_begin, int c_end, int cb0) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // stage buffers, 1 KB aligned
+    __shared__ __align__(8) uint64_t bars[2 * kStages + 1];
+    __shared__ uint32_t tmem_slot;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full = [&](int s) { return bar0 + 8u * s; };
+    auto empty = [&](int s) { return bar0 + 8u * (kStages + s); };
+    const uint32_t tmem_full = bar0 + 8u * (2 * kStages);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile_t = blockIdx.x, cb = cb0 + blockIdx.y;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((uint32_t)kTN)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else if (threadIdx.x == 32) {
+        for (int s = 0; s < kStages; s++) { mbar_init(full(s), 1); mbar_init(empty(s), 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {  // ---- producer: stage kb <- A tile kb, X tile (cb, 4 tile_t + kb)
+            const uint8_t* xsrc = Xt + ((size_t)cb * n_sb + (size_t)tile_t * (kTM / kBK)) * 2 * kBBytes;
+            for (int kb = 0; kb < nK; kb++) {
+                const int s = kb % kStages;
+                mbar_wait(empty(s), ((kb / kStages) & 1) ^ 1);
+                mbar_expect_tx(full(s), kStageBytes);
+                const uint32_t dst = base + s * kStageBytes;
+                bulk_g2s(dst, At + (size_t)kb * 2 * kABytes, 2 * kABytes, full(s));
+                bulk_g2s(dst + 2 * kABytes, xsrc + (size_t)kb * 2 * kBBytes, 2 * kBBytes, full(s));
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {  // ---- MMA issuer
+            for (int kb = 0; kb < nK; kb++) {
+                const int s = kb % kStages;
+                mbar_wait(full(s), (kb / kStages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = base + s * kStageBytes, a_lo = a_hi + kABytes;
+                const uint32_t b_hi = a_hi + 2 * kABytes, b_lo = b_hi + kBBytes;
+#pragma unroll
+                for (int pair = 0; pair < 3; pair++) {
+                    const uint32_t a = pair == 2 ? a_lo : a_hi, b = pair == 1 ? b_lo : b_hi;
+#pragma unroll
+                    for (int k2 = 0; k2 < kBK / 16; k2++) {
+                        const uint64_t ad = umma_desc(a + k2 * 2 * kLBO_A, kLBO_A, kSBO);
+                        const uint64_t bd = umma_desc(b + k2 * 2 * kLBO_B, kLBO_B, kSBO);
+                        umma_bf16(tmem, ad, bd, kIdesc, (kb | pair | k2) != 0);
+                    }
+                }
+                umma_commit(empty(s));  // frees the stage once these MMAs have read it
+            }
+            umma_commit(tmem_full);
+        }
+    } else {  // ---- epilogue: TMEM lane = time row, column = channel
+        const int q = warp & 3;  // the TMEM lane quarter this warp may read
+        const int m = 32 * q + lane;
+        const long long n = (long long)tile_t * kTM + m;
+        mbar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const bool post = post_nf != 0.0f;
+        const int ch0 = cb * kTN;
+#pragma unroll 1
+        for (int col0 = 0; col0 < kTN; col0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)col0, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (n < T) {
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const int ch = ch0 + col0 + j;
+                    if (ch >= c_begin && ch < c_end) {
+                        float y = __fmul_rn(__uint_as_float(v[j]), divisor);
+                        if (post) y = __fdiv_rn(__fadd_rn(0.0f, y), post_nf);  // fused sink fan-in average (node.rs:162-194)
+                        Y[(long long)ch * y_stride + n] = y;
+                    }
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)kTN) : "memory");
+    }
+}
+
+int ceil_to(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+// geometry shared with the engine (buffer sizes)
+int fir_toeplitz_max_taps() { return 16384; }
+static int toep_dmax(int n_taps) { return ceil_to(n_taps - 1, kBK); }
+static int toep_nK(int n_taps) { return toep_dmax(n_taps) / kBK + kTM / kBK; }
+size_t fir_toeplitz_tiles_bytes(int n_taps) { return (size_t)toep_nK(n_taps) * 2 * kABytes; }
+size_t fir_toeplitz_split_bytes(int n_taps, int channels, int64_t max_samples) {
+    const int64_t n_sb = (toep_dmax(n_taps) + (max_samples + kTM - 1) / kTM * kTM) / kBK;
+    return (size_t)((channels + kTN - 1) / kTN) * (size_t)n_sb * 2 * kBBytes;
+}
+
+int fir_toeplitz_prepare(const double* taps_rev_dev, int n_taps, void* tiles_dev, void* stream) {
+    if (n_taps < 1 || n_taps > fir_toeplitz_max_taps()) return (int)cudaErrorInvalidValue;
+    toeplitz_tiles_kernel<<<toep_nK(n_taps), 256, 0, (cudaStream_t)stream>>>(taps_rev_dev, n_taps, toep_dmax(n_taps),
+                                                                           reinterpret_cast<uint8_t*>(tiles_dev));
+    return (int)cudaGetLastError();
+}
+
+int launch_fir_toeplitz(const FirPlan& fp, const float* U, int64_t u_stride, float* Y, int64_t y_stride, int c_begin, int c_end,
+                        int64_t T, cudaStream_t st, int* n_launches) {
+    if (!fp.toep_tiles || !fp.toep_split || fp.n_taps > fir_toeplitz_max_taps()) return (int)cudaErrorInvalidValue;
+    if ((u_stride & 3) || (fp.hist_pad & 3)) return (int)cudaErrorInvalidValue;  // 16-byte aligned row chunks
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(fir_toeplitz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    const int dmax = toep_dmax(fp.n_taps), nK = toep_nK(fp.n_taps);
+    const int n_tiles = (int)((T + kTM - 1) / kTM);
+    const int n_sb_alloc = (int)((dmax + (fp.toep_max_samples + kTM - 1) / kTM * kTM) / kBK);  // tile row pitch of the allocation
+    const int n_sb = dmax / kBK + n_tiles * (kTM / kBK);                                         // tiles this call touches
+    if (n_sb > n_sb_alloc) return (int)cudaErrorInvalidValue;
+    const int cb0 = c_begin / kTN, cb1 = (c_end - 1) / kTN + 1;
+    uint8_t* Xt = reinterpret_cast<uint8_t*>(fp.toep_split);
+    for (int c = cb0; c < cb1; c += 32768) {
+        const int nb = cb1 - c < 32768 ? cb1 - c : 32768;
+        x_split_kernel<<<dim3((unsigned)n_sb, (unsigned)nb), 256, 0, st>>>(U, u_stride, fp.hist_pad, T, dmax, n_sb_alloc, Xt, c_begin, c_end, c);
+        fir_toeplitz_kernel<<<dim3((unsigned)n_tiles, (unsigned)nb), kThreadsT, kSmemBytes, st>>>(
+            reinterpret_cast<const uint8_t*>(fp.toep_tiles), Xt, Y, y_stride, nK, n_sb_alloc, T, fp.divisor, fp.post_nf, c_begin, c_end, c);
+        if (n_launches) *n_launches += 2;
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace dspb

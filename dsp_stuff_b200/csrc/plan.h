@@ -103,9 +103,10 @@ int verify_const_div(float b, float r, unsigned long long* mismatches);
 // debug: summed clock64 phase timings of the warp-specialised kernel (only with -DDSPB_WS_TIMING)
 int ws_timing_read(long long* out8, bool clear);
 
-enum FirMode { FIR_FFT = 0, FIR_DIRECT = 1 };
+enum FirMode { FIR_FFT = 0, FIR_DIRECT = 1, FIR_TOEPLITZ = 2 };
 struct FirPlan {
-    int mode;             // FIR_FFT: overlap-save FFT (f32); FIR_DIRECT: time domain, f64, reference summation order
+    int mode;             // FIR_FFT: overlap-save FFT (f32); FIR_DIRECT: time domain, f64, reference summation order;
+                          // FIR_TOEPLITZ: Toeplitz-tiled tcgen05 GEMM, split bf16 (fir_toeplitz.cu)
     int log2F;            // FFT size F = 1 << log2F complex points, two channels per transform
     int n_taps;           // N
     int hist_pad;         // leading samples kept in U before this call's sample 0 (>= N-1, multiple of 4)
@@ -113,6 +114,11 @@ struct FirPlan {
     const double* taps;   // [N] reversed taps (f64) for the warm-up path
     float divisor;        // 1/N (Average) or 1 (Balanced), fir.rs:187-190
     float post_nf;        // != 0: epilogue y = (0.0 + y) / post_nf, the fan-in average of a sink fed only by this node
+    // FIR_TOEPLITZ only: pre-built Toeplitz tiles of the tap set, scratch for the hi/lo bf16 split of U, and the
+    // max_samples the scratch was sized for
+    const void* toep_tiles = nullptr;
+    void* toep_split = nullptr;
+    int64_t toep_max_samples = 0;
 };
 // U: [C x (hist_pad + T)] input incl. history; Y: [C x T] output.  started = samples seen before this call.
 int launch_fir(const FirPlan& fp, const float* U, int64_t u_stride, float* Y, int64_t y_stride, int c_begin, int c_end,
@@ -120,5 +126,10 @@ int launch_fir(const FirPlan& fp, const float* U, int64_t u_stride, float* Y, in
 // Computes H from the (device-resident, reversed, f64) taps with the kernel's own forward passes in f64.
 int fir_prepare_spectrum(int log2F, const double* taps_rev_dev, int n_taps, float2* H_dev, void* stream);
 int fir_fft_max_taps();
+// Toeplitz tensor-core path (fir_toeplitz.cu): buffer sizes, tile construction for one tap set
+int fir_toeplitz_max_taps();
+size_t fir_toeplitz_tiles_bytes(int n_taps);
+size_t fir_toeplitz_split_bytes(int n_taps, int channels, int64_t max_samples);
+int fir_toeplitz_prepare(const double* taps_rev_dev, int n_taps, void* tiles_dev, void* stream);
 
 }  // namespace dspb

@@ -23,6 +23,7 @@ MEM_DEVICE = 0
 MEM_HOST = 1
 FIR_FFT = 0
 FIR_DIRECT = 1
+FIR_TOEPLITZ = 2
 
 
 class Config(ctypes.Structure):

@@ -62,7 +62,9 @@ typedef struct dspb_config {
     int64_t max_samples;  /* largest n_samples a single dspb_process call will pass; 0 -> 64*block */
     int32_t fir_fft_log2; /* 0 -> engine default (13); FFT size of the overlap-save FIR path */
     int32_t fir_mode;     /* 0 -> overlap-save FFT in f32 (throughput path); 1 -> direct time-domain sum in f64 in
-                             the reference's summation order (bit-exact; 8192 f64 flop/sample at 4096 taps) */
+                             the reference's summation order (bit-exact; 8192 f64 flop/sample at 4096 taps);
+                             2 -> Toeplitz-tiled tensor-core GEMM (tcgen05, split bf16 operands, f32 accumulate;
+                             the comparison path of BASELINE config 4, within the 1e-5 parity bar) */
 } dspb_config;
 
 /* ---- lifetime ----------------------------------------------------------------------------- */

@@ -62,3 +62,41 @@ def test_long_ir_falls_back_to_exact_path(oracle_mod):
     x = S.noise(2, 128 * 50)
     got, ref, eng = run_both(oracle_mod, spec, x, fir_mode=FIR_FFT)
     assert_bit_exact(got[0], ref[0], "long IR uses the direct path")
+
+
+# ---- Toeplitz tensor-core path (csrc/fir_toeplitz.cu): tcgen05 GEMM on hi/lo bf16 operands, f32 accumulate ----
+FIR_TOEPLITZ = 2
+
+
+@pytest.mark.parametrize("n_taps,C,n,chunks", [
+    (4096, 5, 128 * 100, None),                 # one partial channel block, warm-up inside the call
+    (4096, 300, 128 * 48, [128 * 8, 128 * 40]), # two channel blocks (one partial), state carried across calls
+    (300, 3, 128 * 70, [128, 128 * 69]),
+    (1, 2, 128 * 33, None),                     # default taps [1.0]: hi + lo must reproduce x to 2^-17
+    (4500, 2, 128 * 80, None),                  # longer than the FFT path takes
+])
+def test_toeplitz_path_vs_oracle(oracle_mod, n_taps, C, n, chunks):
+    spec = S.config4(n_taps)
+    x = S.noise(C, n)
+    got, ref, eng = run_both(oracle_mod, spec, x, chunks=chunks, fir_mode=FIR_TOEPLITZ)
+    rel, dbfs = assert_audio_close(got[0], ref[0], what=f"fir toeplitz N={n_taps}")
+    w = min(n, n_taps - 1)
+    assert_bit_exact(got[0][:, :w], ref[0][:, :w], "fir warm-up")
+    print(f"fir toeplitz N={n_taps}: peak-relative {rel:.2e}, rms {dbfs:.1f} dBFS")
+
+
+def test_toeplitz_matches_fft_at_full_width():
+    """BASELINE config 4 (4096 channels): the two throughput paths against each other on the device."""
+    C, n = 4096, 128 * 40
+    spec = S.config4(4096)
+    x = S.noise(C, n)
+    a = make_engine(spec, C, n, fir_mode=FIR_FFT).process(x)[0]
+    b = make_engine(spec, C, n, fir_mode=FIR_TOEPLITZ).process(x)[0]
+    assert_audio_close(b, a, what="toeplitz vs fft")
+
+
+def test_target_chain_toeplitz(oracle_mod):
+    spec = S.target_chain(4096)
+    x = S.noise(6, 128 * 120)
+    got, ref, eng = run_both(oracle_mod, spec, x, chunks=[128 * 40, 128 * 80], fir_mode=FIR_TOEPLITZ)
+    assert_audio_close(got[0], ref[0], what="target chain (toeplitz fir)")
