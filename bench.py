@@ -306,7 +306,7 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "channels_per_gpu": C, "samples_per_step": n, "block": args.block,
-                       "blocks_per_step": args.blocks_per_step, "fir_mode": {0: "fft", 1: "direct_f64", 2: "toeplitz_tcgen05_bf16x2"}[args.fir_mode],
+                       "blocks_per_step": args.blocks_per_step, "fir_mode": {0: "fft", 1: "direct_f64", 2: "toeplitz_tcgen05_bf16x2", 3: "fft_packed_f32x2"}[args.fir_mode],
                        "l2_policy": f"inputs+outputs {2 * C * n * 4 / 2**20:.0f} MiB per step exceed the 126 MB L2",
                        "x_realtime_per_channel": value / world / C / 48000.0},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

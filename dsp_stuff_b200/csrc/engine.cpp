@@ -686,9 +686,9 @@ int Lowerer::lower() {
                     }
                 }
                 char b[200];
-                if (e.cfg.fir_mode == FIR_FFT)
-                    snprintf(b, sizeof b, "fir step: %s, %zu taps, overlap-save FFT 2^%d, two channels per transform, alg_bytes=8\n", tag.c_str(),
-                             nd.taps.size(), e.cfg.fir_fft_log2);
+                if (e.cfg.fir_mode == FIR_FFT || e.cfg.fir_mode == FIR_FFT_PACKED)
+                    snprintf(b, sizeof b, "fir step: %s, %zu taps, overlap-save FFT 2^%d%s, two channels per transform, alg_bytes=8\n", tag.c_str(),
+                             nd.taps.size(), e.cfg.fir_fft_log2, e.cfg.fir_mode == FIR_FFT_PACKED ? " (packed f32x2 variant)" : "");
                 else if (e.cfg.fir_mode == FIR_TOEPLITZ)
                     snprintf(b, sizeof b, "fir step: %s, %zu taps, Toeplitz-tiled tcgen05 GEMM 128x256x32, split bf16 (3 MMAs per K step), alg_bytes=8\n",
                              tag.c_str(), nd.taps.size());
@@ -849,7 +849,7 @@ int ensure_resources(dspb_engine* e) {
             }
             int r = n.Y.alloc((size_t)C * maxn * 4, false);
             if (r) return r;
-            r = n.H.alloc((size_t)F * 8, false);
+            r = n.H.alloc((size_t)F * 16, false);  // two spectrum tables (scalar-kernel order, packed-kernel order)
             if (r) return r;
             r = n.taps_dev.alloc((size_t)N * 8, false);
             if (r) return r;
@@ -990,7 +990,7 @@ int run_steps(dspb_engine* e, const float* const* d_in, float* const* d_out, int
             FirPlan fp;
             fp.mode = e->cfg.fir_mode;
             if (fp.mode == FIR_TOEPLITZ && (int)f.taps.size() > fir_toeplitz_max_taps()) fp.mode = FIR_DIRECT;
-            if (fp.mode == FIR_FFT && (int)f.taps.size() > fir_fft_max_taps()) fp.mode = FIR_DIRECT;  // long IRs: exact path
+            if ((fp.mode == FIR_FFT || fp.mode == FIR_FFT_PACKED) && (int)f.taps.size() > fir_fft_max_taps()) fp.mode = FIR_DIRECT;  // long IRs: exact path
             fp.toep_tiles = f.toep_tiles.p;
             fp.toep_split = f.toep_split.p;
             fp.toep_max_samples = e->cfg.max_samples;
@@ -1075,9 +1075,9 @@ int dspb_engine_create(const dspb_config* cfg, dspb_engine** out) {
     e->cfg.max_samples = round_up(e->cfg.max_samples, kRefBlock);
     if (e->cfg.fir_fft_log2 <= 0) e->cfg.fir_fft_log2 = 13;
     if (e->cfg.fir_fft_log2 != 13) { delete e; return fail(DSPB_ERR_INVALID, "fir_fft_log2 must be 13 in this build"); }
-    if (e->cfg.fir_mode != FIR_FFT && e->cfg.fir_mode != FIR_DIRECT && e->cfg.fir_mode != FIR_TOEPLITZ) {
+    if (e->cfg.fir_mode < FIR_FFT || e->cfg.fir_mode > FIR_FFT_PACKED) {
         delete e;
-        return fail(DSPB_ERR_INVALID, "fir_mode must be 0 (FFT), 1 (direct) or 2 (Toeplitz tensor-core)");
+        return fail(DSPB_ERR_INVALID, "fir_mode must be 0 (FFT), 1 (direct), 2 (Toeplitz tensor-core) or 3 (packed FFT)");
     }
     if (const char* g = getenv("DSPB_FORCE_G")) e->force_G = atoi(g);
     if (const char* g = getenv("DSPB_CHUNKS")) e->dev_chunks = std::max(1, std::min(8, atoi(g)));

@@ -227,6 +227,15 @@ __device__ __forceinline__ void inv_pass8(C2<T>* a, const Tw<T>& W, int t) {
 // first / last pass move two consecutive samples per 64-bit access.
 // post: optional epilogue "acc = 0.0 + y; acc /= post_nf" = the fan-in average of a sink fed only by this
 // node (node.rs:162-194, nodes/output.rs:223), so no separate kernel has to touch the output again.
+// (0.0 + y) / nf with Markstein's three-instruction sequence (exact_math.cuh: correctly rounded except in the
+// denormal / overflow fringes, where it is one ulp off -- far inside this path's 1e-5 tolerance) instead of the
+// ~10-instruction IEEE division: the division was 7 % of this kernel's issued instructions.
+__device__ __forceinline__ float div_nf(float y, float nf, float rnf) {
+    const float a = __fadd_rn(0.0f, y);
+    const float q0 = __fmul_rn(a, rnf);
+    return __fmaf_rn(__fmaf_rn(-q0, nf, a), rnf, q0);
+}
+
 __global__ void __launch_bounds__(kNT, 3)
 fir_fft_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, float* __restrict__ Y, long long y_stride,
                const float2* __restrict__ Hg, const float2* __restrict__ Wg, int Ne, long long T, float divisor, float post_nf,
@@ -318,6 +327,7 @@ fir_fft_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, fl
         float* outA = Y + (long long)chA * y_stride + s0 - (Ne - 1);
         float* outB = Y + (long long)chB * y_stride + s0 - (Ne - 1);
         const bool post = post_nf != 0.0f;
+        const float post_rnf = post ? __frcp_rn(post_nf) : 0.0f;
 #pragma unroll 1
         for (int k = 0; k < kF / 8 / kNT / 2; k++) {
             const int j = 2 * (t + kNT * k);
@@ -341,8 +351,8 @@ fir_fft_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, fl
                     float2 ya = make_float2(__fmul_rn(v0[r].x, divisor), __fmul_rn(v1[r].x, divisor));
                     float2 yb = make_float2(__fmul_rn(v0[r].y, divisor), __fmul_rn(v1[r].y, divisor));
                     if (post) {
-                        ya.x = __fdiv_rn(__fadd_rn(0.0f, ya.x), post_nf); ya.y = __fdiv_rn(__fadd_rn(0.0f, ya.y), post_nf);
-                        yb.x = __fdiv_rn(__fadd_rn(0.0f, yb.x), post_nf); yb.y = __fdiv_rn(__fadd_rn(0.0f, yb.y), post_nf);
+                        ya.x = div_nf(ya.x, post_nf, post_rnf); ya.y = div_nf(ya.y, post_nf, post_rnf);
+                        yb.x = div_nf(yb.x, post_nf, post_rnf); yb.y = div_nf(yb.y, post_nf, post_rnf);
                     }
                     *reinterpret_cast<float2*>(outA + n) = ya;
                     if (hasB) *reinterpret_cast<float2*>(outB + n) = yb;
@@ -350,6 +360,303 @@ fir_fft_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, fl
             }
         }
     }
+}
+
+// ======================= packed variant: two sub-transforms per register pair =======================
+// One radix-2 decimation-in-frequency step turns the F = 8192 point transform of z into two INDEPENDENT
+// 4096-point transforms (E[n] = z[n] + z[n+4096] -> even bins, O[n] = (z[n] - z[n+4096]) W_F^n -> odd bins)
+// with identical structure and twiddles.  They are carried side by side in 64-bit register pairs
+// (re = (E.re, O.re), im = (E.im, O.im)) through four radix-8 passes, the spectrum product and four inverse
+// passes, so every butterfly add, twiddle multiply, shared-memory access and index computation is issued ONCE
+// for both (add/mul/fma.rn.f32x2).  MEASURED OUTCOME (B200, profiles/r01s3_target_fir_fft_packed_kernel.txt): this
+// kernel issues 16 % fewer warp-instructions than the scalar kernel above (266 M vs 315 M per launch) but runs
+// 0.441 ms against 0.412 ms: the packed instructions occupy the FP32 pipe for two cycles each and have longer
+// dependent-issue latency (tests/cuda/f32x2_microbench.cu: 2.0 packed vs 3.7 scalar FFMA per clock per SM), so
+// with 24 warps per SM the kernel becomes latency-bound (issue-active 55 %, FP32 pipe 44 %) instead of
+// issue-bound (70 %).  It therefore stays an opt-in (fir_mode = 3) and the scalar kernel is the default.
+// Only the upper half of the circular convolution is valid with 4096 + 1 taps, and
+// z[n + 4096] = E'[n] - W_F^-n O'[n] is exactly the half the last radix-2 step has to produce.
+// Shared memory: 4096 float4 (E.re, O.re, E.im, O.im) with an XOR swizzle of the low three index bits (no
+// padding), + the twiddle tables stored duplicated (wr, wr, wi, wi) so one LDS.128 yields packed operands.
+typedef unsigned long long u64;
+constexpr int kH2 = kF / 2;  // points of each sub-transform
+struct VF { u64 re, im; };   // packed complex pair: lo half = E, hi half = O
+struct WF { u64 re, im; };   // one twiddle, duplicated into both halves
+__device__ __forceinline__ u64 pk(float lo, float hi) { return (u64)__float_as_uint(lo) | ((u64)__float_as_uint(hi) << 32); }
+__device__ __forceinline__ float lo32(u64 a) { return __uint_as_float((unsigned)a); }
+__device__ __forceinline__ float hi32(u64 a) { return __uint_as_float((unsigned)(a >> 32)); }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 neg2(u64 a) { return a ^ 0x8000000080000000ull; }  // integer pipe: free next to the FP32 pipe
+__device__ __forceinline__ VF operator+(VF a, VF b) { return {add2(a.re, b.re), add2(a.im, b.im)}; }
+__device__ __forceinline__ VF operator-(VF a, VF b) { return {sub2(a.re, b.re), sub2(a.im, b.im)}; }
+// a * w and a * conj(w); the factor may differ per half (spectrum product) or be duplicated (twiddles)
+__device__ __forceinline__ VF vmul(VF a, u64 wre, u64 wim) { return {fma2(neg2(a.im), wim, mul2(a.re, wre)), fma2(a.re, wim, mul2(a.im, wre))}; }
+__device__ __forceinline__ VF vmulc(VF a, u64 wre, u64 wim) { return {fma2(a.im, wim, mul2(a.re, wre)), fma2(neg2(a.re), wim, mul2(a.im, wre))}; }
+__device__ __forceinline__ WF wmul(WF a, WF b) { const VF r = vmul(VF{a.re, a.im}, b.re, b.im); return {r.re, r.im}; }
+
+// a * w_SZ^I for the rotations a radix-8 butterfly needs (SZ in {2, 4, 8})
+template <int SZ, int I, bool INV>
+__device__ __forceinline__ VF vtw(VF a) {
+    if constexpr (I == 0) {
+        return a;
+    } else if constexpr (4 * I == SZ) {
+        if constexpr (INV) return {neg2(a.im), a.re};
+        else return {a.im, neg2(a.re)};
+    } else {
+        static_assert(SZ == 8 && (I == 1 || I == 3), "radix-8 rotations only");
+        const u64 h = pk(0.70710678118654752440f, 0.70710678118654752440f), nh = neg2(h);
+        if constexpr (I == 1) {
+            if constexpr (INV) return {mul2(sub2(a.re, a.im), h), mul2(add2(a.re, a.im), h)};
+            else return {mul2(add2(a.re, a.im), h), mul2(sub2(a.im, a.re), h)};
+        } else {
+            if constexpr (INV) return {mul2(add2(a.re, a.im), nh), mul2(sub2(a.re, a.im), h)};
+            else return {mul2(sub2(a.im, a.re), h), mul2(add2(a.re, a.im), nh)};
+        }
+    }
+}
+// Radix-8 butterflies written out so that the +-i rotations fold into the choice of add / sub of the next stage
+// (a negation of a packed pair would cost two LOP3).
+// x + (-i) y and x - (-i) y;  x + (i) y and x - (i) y
+__device__ __forceinline__ VF add_mi(VF x, VF y) { return {add2(x.re, y.im), sub2(x.im, y.re)}; }
+__device__ __forceinline__ VF sub_mi(VF x, VF y) { return {sub2(x.re, y.im), add2(x.im, y.re)}; }
+__device__ __forceinline__ void fft_dif8v(VF (&v)[8]) {  // natural in, bit-reversed out (v[s] = bin bitrev3(s))
+    const VF a0 = v[0] + v[4], a1 = v[1] + v[5], a2 = v[2] + v[6], a3 = v[3] + v[7];
+    const VF b0 = v[0] - v[4], b2 = v[2] - v[6];
+    const VF b1 = vtw<8, 1, false>(v[1] - v[5]), b3 = vtw<8, 3, false>(v[3] - v[7]);
+    const VF c0 = a0 + a2, c1 = a1 + a3, d0 = a0 - a2, d1 = a1 - a3;        // d1 still lacks its factor -i
+    const VF e0 = add_mi(b0, b2), e1 = b1 + b3, f0 = sub_mi(b0, b2), f1 = b1 - b3;  // b2 (-i) folded; f1 lacks -i
+    v[0] = c0 + c1; v[1] = c0 - c1;
+    v[2] = add_mi(d0, d1); v[3] = sub_mi(d0, d1);
+    v[4] = e0 + e1; v[5] = e0 - e1;
+    v[6] = add_mi(f0, f1); v[7] = sub_mi(f0, f1);
+}
+__device__ __forceinline__ void ifft_dit8v(VF (&v)[8]) {  // exact mirror: bit-reversed in, natural out, conjugate rotations
+    const VF c0 = v[0] + v[1], c1 = v[0] - v[1], d0 = v[2] + v[3], d1 = v[2] - v[3];  // d1 lacks its factor +i
+    const VF e0 = v[4] + v[5], e1 = v[4] - v[5], f0 = v[6] + v[7], f1 = v[6] - v[7];  // f1 lacks +i
+    const VF a0 = c0 + d0, a2 = c0 - d0, a1 = sub_mi(c1, d1), a3 = add_mi(c1, d1);   // x + i y = sub_mi(x, y)
+    const VF b0 = e0 + f0, b2 = e0 - f0;                                             // b2 lacks +i
+    const VF b1 = vtw<8, 1, true>(sub_mi(e1, f1)), b3 = vtw<8, 3, true>(add_mi(e1, f1));
+    v[0] = a0 + b0; v[4] = a0 - b0;
+    v[1] = a1 + b1; v[5] = a1 - b1;
+    v[2] = sub_mi(a2, b2); v[6] = add_mi(a2, b2);
+    v[3] = a3 + b3; v[7] = a3 - b3;
+}
+__device__ __forceinline__ int swz8(int p) { return p ^ ((p >> 3) & 7); }
+// explicit 128-bit accesses straight into / out of the two 64-bit register pairs (left to itself the compiler splits
+// the float4 into two LDS.64, which at a 16-byte lane stride are two-way bank conflicts)
+__device__ __forceinline__ VF ld_vf(const float4* a, int p) {
+    VF v;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v.re), "=l"(v.im) : "r"((unsigned)__cvta_generic_to_shared(a + swz8(p))));
+    return v;
+}
+__device__ __forceinline__ void st_vf(float4* a, int p, VF v) {
+    asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"((unsigned)__cvta_generic_to_shared(a + swz8(p))), "l"(v.re), "l"(v.im) : "memory");
+}
+
+// duplicated twiddle tables in shared memory: W_F^k = coarse[k >> 4] * fine[k & 15]
+struct TwP {
+    const float4* coarse;  // [512]
+    const float4* fine;    // [16]
+    __device__ __forceinline__ WF c(int m) const {
+        WF w;
+        asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(w.re), "=l"(w.im) : "r"((unsigned)__cvta_generic_to_shared(coarse + (m & (kCoarse - 1)))));
+        return w;
+    }
+    __device__ __forceinline__ WF at(int k) const {
+        const float4 q = fine[k & 15];
+        return wmul(c(k >> 4), WF{pk(q.x, q.y), pk(q.z, q.w)});
+    }
+    __device__ __forceinline__ C2<float> scalar(int k) const {  // W_F^k as one scalar complex
+        const float4 a = coarse[(k >> 4) & (kCoarse - 1)], b = fine[k & 15];
+        return cmul(C2<float>{a.x, a.z}, C2<float>{b.x, b.z});
+    }
+};
+// w[q] = w1^q for q = 1..7 from w1, w2, w4
+__device__ __forceinline__ void powers8(WF w1, WF w2, WF w4, WF (&w)[8]) {
+    w[1] = w1; w[2] = w2; w[4] = w4;
+    w[3] = wmul(w1, w2);
+    w[5] = wmul(w1, w4);
+    w[6] = wmul(w2, w4);
+    w[7] = wmul(w[3], w4);
+}
+// forward / inverse radix-8 pass on the shared array, sub-transform size M in {512, 64}: both butterflies of a
+// thread share j, so the twiddles are computed once
+template <int M>
+__device__ __forceinline__ void fwd_pass8v(float4* a, const TwP& W, int t) {
+    constexpr int L = M / 8, CS = (kF / 16) / M;  // coarse-table step of W_M
+    const int j = t % L;
+    WF w[8];
+    powers8(W.c(j * CS), W.c(2 * j * CS), W.c(4 * j * CS), w);
+#pragma unroll 1
+    for (int k = 0; k < kH2 / 8 / kNT; k++) {
+        const int u = t + kNT * k, base = (u / L) * M + j;
+        VF v[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) v[r] = ld_vf(a, base + r * L);
+        fft_dif8v(v);
+        st_vf(a, base, v[0]);
+#pragma unroll
+        for (int s = 1; s < 8; s++) st_vf(a, base + bitrev3(s) * L, vmul(v[s], w[bitrev3(s)].re, w[bitrev3(s)].im));
+    }
+}
+template <int M>
+__device__ __forceinline__ void inv_pass8v(float4* a, const TwP& W, int t) {
+    constexpr int L = M / 8, CS = (kF / 16) / M;
+    const int j = t % L;
+    WF w[8];
+    powers8(W.c(j * CS), W.c(2 * j * CS), W.c(4 * j * CS), w);
+#pragma unroll 1
+    for (int k = 0; k < kH2 / 8 / kNT; k++) {
+        const int u = t + kNT * k, base = (u / L) * M + j;
+        VF v[8];
+        v[0] = ld_vf(a, base);
+#pragma unroll
+        for (int s = 1; s < 8; s++) v[s] = vmulc(ld_vf(a, base + bitrev3(s) * L), w[bitrev3(s)].re, w[bitrev3(s)].im);
+        ifft_dit8v(v);
+#pragma unroll
+        for (int r = 0; r < 8; r++) st_vf(a, base + r * L, v[r]);
+    }
+}
+
+// Window of segment s: call-relative samples [4096 (s - 1), 4096 (s + 1)); outputs [4096 s, 4096 (s + 1)).
+// Requires n_taps <= 4097 (taps beyond the stored history multiply zeros: samples before -hist_pad read as 0).
+__global__ void __launch_bounds__(kNT, 3)
+fir_fft_packed_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, float* __restrict__ Y, long long y_stride,
+                      const float4* __restrict__ Hg, const float2* __restrict__ Wg, long long T, float divisor, float post_nf,
+                      int c_begin, int c_end) {
+    extern __shared__ float4 smem_f4[];
+    float4* a = smem_f4;  // [4096]
+    float4* tab = a + kH2;
+    const int t = threadIdx.x;
+    for (int i = t; i < kCoarse; i += kNT) { const float2 w = Wg[16 * i]; tab[i] = make_float4(w.x, w.x, w.y, w.y); }
+    if (t < kFine) { const float2 w = Wg[t]; tab[kCoarse + t] = make_float4(w.x, w.x, w.y, w.y); }
+    const TwP W{tab, tab + kCoarse};
+    const long long s0 = (long long)blockIdx.x * kH2;
+    const int chA = c_begin + 2 * blockIdx.y, chB = chA + 1;
+    const bool hasB = chB < c_end;
+    const float* rowA = U + (long long)chA * u_stride + hist_pad + (s0 - kH2);
+    const float* rowB = U + (long long)(hasB ? chB : chA) * u_stride + hist_pad + (s0 - kH2);
+    // window samples below lo precede the stored history, samples >= lim lie beyond this call's input: zeros.
+    // 0 <= lo <= 4096 < lim <= 8192 after clamping, so [lo, lim) is never empty and clamped indices are loadable.
+    const long long lo_ll = -(long long)hist_pad - (s0 - kH2), lim_ll = T - (s0 - kH2);
+    const int lo = lo_ll < 0 ? 0 : (int)lo_ll, lim = lim_ll > kF ? kF : (int)lim_ll;
+    __syncthreads();
+
+    // ---- forward pass 0: global -> radix-2 split -> radix-8 (M = 4096) -> shared
+#pragma unroll 1
+    for (int k = 0; k < kH2 / 8 / kNT; k++) {
+        const int j = t + kNT * k;
+        const C2<float> wj = W.scalar(j);
+        VF v[8];
+        static_for<8>([&](auto rr) {
+            constexpr int r = decltype(rr)::value;
+            const int n = j + r * (kH2 / 8);
+            // branch-free (clamped index, select afterwards) so that all 32 loads of a butterfly are issued back to back
+            const int i0 = min(max(n, lo), lim - 1), i1 = min(n + kH2, lim - 1);  // n + 4096 >= lo always
+            const bool ok0 = n >= lo && n < lim, ok1 = n + kH2 < lim;
+            float a0 = __ldg(rowA + i0), b0 = __ldg(rowB + i0), a1 = __ldg(rowA + i1), b1 = __ldg(rowB + i1);
+            a0 = ok0 ? a0 : 0.f; b0 = (ok0 && hasB) ? b0 : 0.f; a1 = ok1 ? a1 : 0.f; b1 = (ok1 && hasB) ? b1 : 0.f;
+            const C2<float> d = tw<16, r, false, float>(cmul(C2<float>{a0 - a1, b0 - b1}, wj));  // (z[n] - z[n+4096]) W_F^(j + 512 r)
+            v[r] = VF{pk(a0 + a1, d.x), pk(b0 + b1, d.y)};
+        });
+        fft_dif8v(v);
+        WF w[8];
+        powers8(W.at(2 * j), W.at(4 * j), W.at(8 * j), w);
+        st_vf(a, j, v[0]);
+#pragma unroll
+        for (int s = 1; s < 8; s++) st_vf(a, j + bitrev3(s) * (kH2 / 8), vmul(v[s], w[bitrev3(s)].re, w[bitrev3(s)].im));
+    }
+    __syncthreads();
+    fwd_pass8v<kH2 / 8>(a, W, t);
+    __syncthreads();
+    fwd_pass8v<kH2 / 64>(a, W, t);
+    __syncthreads();
+    // ---- pass 3 (radix 8, no twiddles) . spectrum product . inverse pass 3, in registers
+#pragma unroll 1
+    for (int k = 0; k < kH2 / 8 / kNT; k++) {
+        const int base = 8 * (t + kNT * k);
+        const float4* h4 = Hg + (k * 8) * kNT + t;  // [k][s][thread]: (H_even.re, H_odd.re, H_even.im, H_odd.im)
+        float4 h[8];
+#pragma unroll
+        for (int s = 0; s < 8; s++) h[s] = __ldg(h4 + s * kNT);
+        VF v[8];
+#pragma unroll
+        for (int s = 0; s < 8; s++) v[s] = ld_vf(a, base + s);
+        fft_dif8v(v);
+#pragma unroll
+        for (int s = 0; s < 8; s++) v[s] = vmul(v[s], pk(h[s].x, h[s].y), pk(h[s].z, h[s].w));
+        ifft_dit8v(v);
+#pragma unroll
+        for (int s = 0; s < 8; s++) st_vf(a, base + s, v[s]);
+    }
+    __syncthreads();
+    inv_pass8v<kH2 / 64>(a, W, t);
+    __syncthreads();
+    inv_pass8v<kH2 / 8>(a, W, t);
+    __syncthreads();
+    // ---- inverse pass 0: shared -> radix-8 -> last radix-2 step (upper half only) -> global
+    {
+        float* outA = Y + (long long)chA * y_stride + s0;
+        float* outB = Y + (long long)chB * y_stride + s0;
+        const bool post = post_nf != 0.0f;
+        const float post_rnf = post ? __frcp_rn(post_nf) : 0.0f;
+        const long long out_lim = T - s0;
+#pragma unroll 1
+        for (int k = 0; k < kH2 / 8 / kNT; k++) {
+            const int j = t + kNT * k;
+            WF w[8];
+            powers8(W.at(2 * j), W.at(4 * j), W.at(8 * j), w);
+            VF v[8];
+            v[0] = ld_vf(a, j);
+#pragma unroll
+            for (int s = 1; s < 8; s++) v[s] = vmulc(ld_vf(a, j + bitrev3(s) * (kH2 / 8)), w[bitrev3(s)].re, w[bitrev3(s)].im);
+            ifft_dit8v(v);
+            const C2<float> wj = W.scalar(j);
+            static_for<8>([&](auto rr) {
+                constexpr int r = decltype(rr)::value;
+                const int n = j + r * (kH2 / 8);
+                const C2<float> o = tw<16, r, true, float>(cmulc(C2<float>{hi32(v[r].re), hi32(v[r].im)}, wj));  // O'[n] W_F^-(j + 512 r)
+                float ya = __fmul_rn(lo32(v[r].re) - o.x, divisor), yb = __fmul_rn(lo32(v[r].im) - o.y, divisor);
+                if (post) { ya = div_nf(ya, post_nf, post_rnf); yb = div_nf(yb, post_nf, post_rnf); }
+                if (n < out_lim) {
+                    outA[n] = ya;
+                    if (hasB) outB[n] = yb;
+                }
+            });
+        }
+    }
+}
+
+// Spectrum for the packed kernel: bin f of the zero-padded impulse response by direct f64 summation (exact
+// argument reduction: f n mod F is an integer), scaled by 1/F, stored where pass 3 of the packed kernel finds
+// it: float4 [(k * 8 + s) * 256 + t] = (H[2 f'].re, H[2 f' + 1].re, H[2 f'].im, H[2 f' + 1].im) with
+// f' = d3 + 8 d2 + 64 d1 + 512 d0, (d3, d2, d1) the base-8 digits of u = t + 256 k, d0 = bitrev3(s).
+__global__ void fir_spectrum_packed_kernel(const double* __restrict__ taps_rev, int N, float4* __restrict__ Hout) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // [k][s][t]
+    if (idx >= kH2) return;
+    const int tt = idx % kNT, s = (idx / kNT) % 8, k = idx / (8 * kNT);
+    const int u = tt + kNT * k;
+    const int d3 = u / 64, d2 = (u / 8) % 8, d1 = u % 8, d0 = bitrev3(s);
+    const int fp = d3 + 8 * d2 + 64 * d1 + 512 * d0;
+    double acc[4] = {0, 0, 0, 0};
+    for (int half = 0; half < 2; half++) {
+        const int f = 2 * fp + half;
+        double re = 0.0, im = 0.0;
+        for (int n = 0; n < N; n++) {
+            const int m = (int)(((long long)f * n) & (kF - 1));
+            double sn, cs;
+            sincospi(-2.0 * (double)m / (double)kF, &sn, &cs);
+            const double h = taps_rev[N - 1 - n];  // h[n] = taps[N-1-n] (fir.rs:163-168)
+            re += h * cs;
+            im += h * sn;
+        }
+        acc[half] = re / kF;
+        acc[2 + half] = im / kF;
+    }
+    Hout[idx] = make_float4((float)acc[0], (float)acc[1], (float)acc[2], (float)acc[3]);
 }
 
 // ---- spectrum of h in the transform's own output order (f64), scaled by 1/F -----------------------------
@@ -417,6 +724,25 @@ int launch_fir_fft(const FirPlan& fp, const float* U, int64_t u_stride, float* Y
     if (fp.log2F != kLog2F || fp.n_taps > fir_fft_max_taps() || fp.n_taps < 1) return (int)cudaErrorInvalidValue;
     int rc = ensure_tables();
     if (rc) return rc;
+    if (fp.mode == FIR_FFT_PACKED) {  // opt-in: measured 5 % slower than the scalar kernel (see the comment above VF)
+        static bool configured2 = false;
+        const int smem2 = (kH2 + kCoarse + kFine) * (int)sizeof(float4);
+        if (!configured2) {
+            cudaError_t e = cudaFuncSetAttribute(fir_fft_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
+            if (e != cudaSuccess) return (int)e;
+            configured2 = true;
+        }
+        const long long n_seg2 = (T + kH2 - 1) / kH2;
+        const int pairs2 = (c_end - c_begin + 1) / 2;
+        const float4* Hp = reinterpret_cast<const float4*>(fp.H + kF);  // packed-order spectrum follows the v1 table
+        for (int p0 = 0; p0 < pairs2; p0 += 65535) {
+            dim3 grid((unsigned)n_seg2, (unsigned)std::min(65535, pairs2 - p0));
+            fir_fft_packed_kernel<<<grid, kNT, smem2, st>>>(U, u_stride, fp.hist_pad, Y, y_stride, Hp, g_tab.Wf, T, fp.divisor, fp.post_nf,
+                                                           c_begin + 2 * p0, c_end);
+            if (n_launches) *n_launches += 1;
+        }
+        return (int)cudaGetLastError();
+    }
     static bool configured = false;
     const int smem = (kPadded + kCoarse + kFine) * (int)sizeof(float2);
     if (!configured) {
@@ -445,6 +771,7 @@ int fir_prepare_spectrum(int log2F, const double* taps_rev_dev, int n_taps, floa
     cudaError_t e = cudaFuncSetAttribute(fir_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     fir_spectrum_kernel<<<1, kNT, smem, (cudaStream_t)stream>>>(taps_rev_dev, n_taps, g_tab.Wd, H_dev);
+    fir_spectrum_packed_kernel<<<kH2 / 128, 128, 0, (cudaStream_t)stream>>>(taps_rev_dev, n_taps, reinterpret_cast<float4*>(H_dev + kF));
     return (int)cudaGetLastError();
 }
 

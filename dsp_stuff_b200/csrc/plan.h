@@ -103,14 +103,16 @@ int verify_const_div(float b, float r, unsigned long long* mismatches);
 // debug: summed clock64 phase timings of the warp-specialised kernel (only with -DDSPB_WS_TIMING)
 int ws_timing_read(long long* out8, bool clear);
 
-enum FirMode { FIR_FFT = 0, FIR_DIRECT = 1, FIR_TOEPLITZ = 2 };
+enum FirMode { FIR_FFT = 0, FIR_DIRECT = 1, FIR_TOEPLITZ = 2, FIR_FFT_PACKED = 3 };
 struct FirPlan {
     int mode;             // FIR_FFT: overlap-save FFT (f32); FIR_DIRECT: time domain, f64, reference summation order;
-                          // FIR_TOEPLITZ: Toeplitz-tiled tcgen05 GEMM, split bf16 (fir_toeplitz.cu)
+                          // FIR_TOEPLITZ: Toeplitz-tiled tcgen05 GEMM, split bf16 (fir_toeplitz.cu);
+                          // FIR_FFT_PACKED: the FFT path with two sub-transforms per f32x2 register pair (experiment)
     int log2F;            // FFT size F = 1 << log2F complex points, two channels per transform
     int n_taps;           // N
     int hist_pad;         // leading samples kept in U before this call's sample 0 (>= N-1, multiple of 4)
-    const float2* H;      // [F] spectrum of h in the transform's own output order, pre-scaled by 1/F
+    const float2* H;      // [2F] spectrum of h pre-scaled by 1/F: [0, F) in the scalar kernel's output order, then F/2 float4
+                          // (even bin, odd bin) pairs in the packed kernel's order
     const double* taps;   // [N] reversed taps (f64) for the warm-up path
     float divisor;        // 1/N (Average) or 1 (Balanced), fir.rs:187-190
     float post_nf;        // != 0: epilogue y = (0.0 + y) / post_nf, the fan-in average of a sink fed only by this node

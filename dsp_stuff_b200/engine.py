@@ -24,6 +24,7 @@ MEM_HOST = 1
 FIR_FFT = 0
 FIR_DIRECT = 1
 FIR_TOEPLITZ = 2
+FIR_FFT_PACKED = 3
 
 
 class Config(ctypes.Structure):

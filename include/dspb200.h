@@ -64,7 +64,8 @@ typedef struct dspb_config {
     int32_t fir_mode;     /* 0 -> overlap-save FFT in f32 (throughput path); 1 -> direct time-domain sum in f64 in
                              the reference's summation order (bit-exact; 8192 f64 flop/sample at 4096 taps);
                              2 -> Toeplitz-tiled tensor-core GEMM (tcgen05, split bf16 operands, f32 accumulate;
-                             the comparison path of BASELINE config 4, within the 1e-5 parity bar) */
+                             the comparison path of BASELINE config 4, within the 1e-5 parity bar);
+                             3 -> experimental FFT variant carrying two sub-transforms per f32x2 register pair */
 } dspb_config;
 
 /* ---- lifetime ----------------------------------------------------------------------------- */

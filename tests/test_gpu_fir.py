@@ -100,3 +100,21 @@ def test_target_chain_toeplitz(oracle_mod):
     x = S.noise(6, 128 * 120)
     got, ref, eng = run_both(oracle_mod, spec, x, chunks=[128 * 40, 128 * 80], fir_mode=FIR_TOEPLITZ)
     assert_audio_close(got[0], ref[0], what="target chain (toeplitz fir)")
+
+
+# ---- packed FFT variant (fir_mode 3): two sub-transforms per f32x2 register pair, same tolerance as the FFT path ----
+FIR_FFT_PACKED = 3
+
+
+@pytest.mark.parametrize("n_taps,C,n,chunks", [
+    (4096, 5, 128 * 160, None),
+    (4097, 4, 128 * 96, [128 * 8, 128 * 88]),
+    (300, 3, 128 * 70, [128, 128 * 69]),       # history shorter than the 4096-sample window overlap
+    (1, 2, 128 * 65, None),
+])
+def test_packed_fft_path_vs_oracle(oracle_mod, n_taps, C, n, chunks):
+    spec = S.config4(n_taps)
+    x = S.noise(C, n)
+    got, ref, eng = run_both(oracle_mod, spec, x, chunks=chunks, fir_mode=FIR_FFT_PACKED)
+    rel, dbfs = assert_audio_close(got[0], ref[0], what=f"fir packed fft N={n_taps}")
+    print(f"fir packed fft N={n_taps}: peak-relative {rel:.2e}, rms {dbfs:.1f} dBFS")
