@@ -48,7 +48,7 @@ int fail(int code, const char* fmt, ...) {
 
 // ---- node registry: verbatim mirror of the #[dsp(...)] blocks -------------------
 enum TypeId { T_GAIN, T_DISTORT, T_OVERDRIVE, T_CHEBY, T_BIQUAD, T_LOWPASS, T_HIGHPASS, T_REVERB, T_FIR,
-              T_ADD, T_MIX, T_MUX, T_DEMUX, T_ENVELOPE, T_SIGGEN, T_INPUT, T_OUTPUT, T_COUNT };
+              T_ADD, T_MIX, T_MUX, T_DEMUX, T_ENVELOPE, T_SIGGEN, T_GATE, T_INPUT, T_OUTPUT, T_COUNT };
 
 struct ParamDef {
     const char* name;
@@ -97,6 +97,9 @@ const NodeType kNodeTypes[T_COUNT] = {
     {"signal_gen", {"amplitude", "frequency"}, {"out"},
      {{"amplitude", 0.5f, -1.f, 1.f, 0}, {"frequency", 100.0f, 0.1f, 20000.f, 1}},
      {{"mode", {"Sine", "Triangle", "Square", "Constant"}, 0}}},
+    /* gate       EXTENSION, not a reference node (north_star names a noise gate, the reference has none):
+                  out = envelope(in) >= threshold ? in : 0 with nodes/envelope.rs's detector (attack / release in frames) */
+    {"gate", {"in"}, {"out"}, {{"threshold", 0.f, 0.f, 1.f, -1}, {"attack", 0.f, 0.f, 1000.f, -1}, {"release", 0.f, 0.f, 1000.f, -1}}, {}},
     /* input      nodes/input.rs:12-22    */ {"input", {}, {"out"}, {}, {}},
     /* output     nodes/output.rs:12-22   */ {"output", {"in"}, {}, {}, {}},
 };
@@ -274,7 +277,7 @@ void biquad_regenerate(Node& n) {  // BiQuad::regenerate_filter, nodes/biquad.rs
 }
 
 bool is_stateful(int type) {
-    return type == T_BIQUAD || type == T_LOWPASS || type == T_HIGHPASS || type == T_ENVELOPE || type == T_SIGGEN;
+    return type == T_BIQUAD || type == T_LOWPASS || type == T_HIGHPASS || type == T_ENVELOPE || type == T_SIGGEN || type == T_GATE;
 }
 
 int clear_node_state(dspb_engine* e, Node& n) {
@@ -416,7 +419,7 @@ struct Lowerer {
 // Peephole + vreg allocation for one fused step.  Virtual vregs -> shared-memory slots by liveness.
 int Lowerer::finish_vregs(Step& st, std::vector<Op>& o, std::vector<std::string>& t) {
     auto reads = [](const Op& op, int v) {
-        if ((op.code == OP_LOADV || op.code == OP_ADDV || op.code == OP_COPYV || op.code == OP_ADD || op.code == OP_MIX) && op.vreg == v) return true;
+        if ((op.code == OP_LOADV || op.code == OP_ADDV || op.code == OP_COPYV || op.code == OP_ADD || op.code == OP_MIX || op.code == OP_GATE) && op.vreg == v) return true;
         for (int i = 0; i < 3; i++)
             if ((op.pflags & (1 << i)) && op.pv[i] == v) return true;
         return false;
@@ -735,6 +738,23 @@ int Lowerer::lower() {
                 op.vreg = (uint8_t)vb;
                 emit(op, nd.type == T_ADD ? "acc = acc + v" + std::to_string(vb) + "            ; " + tag
                                           : "acc = v" + std::to_string(vb) + "*r + acc*(1-r)      ; " + tag);
+                values[{ni, 0}] = out_value(0);
+            } break;
+            case T_GATE: {  // extension: x -> vreg, envelope(x) (nodes/envelope.rs arithmetic) -> compare -> select
+                emit_avg(ni, 0);
+                const int vx = temp_save(tag + ".x");
+                Op env = mk(OP_ENVELOPE);
+                env.p[0] = nd.f32[1] == 0.0f ? 0.0f : std::exp(-1.0f / nd.f32[1]);  // dasp calc_gain
+                env.p[1] = nd.f32[2] == 0.0f ? 0.0f : std::exp(-1.0f / nd.f32[2]);
+                if (alloc_state(env) < 0) return DSPB_ERR_INVALID;
+                char b[160];
+                snprintf(b, sizeof b, "acc = envelope(acc; ga=%g gr=%g) exact, lane=channel  ; %s", env.p[0], env.p[1], tag.c_str());
+                emit(env, b);
+                Op g = mk(OP_GATE);
+                g.vreg = (uint8_t)vx;
+                g.p[0] = nd.f32[0];
+                snprintf(b, sizeof b, "acc = acc >= %g ? v%d : 0     ; %s (extension)", nd.f32[0], vx, tag.c_str());
+                emit(g, b);
                 values[{ni, 0}] = out_value(0);
             } break;
             case T_SIGGEN: {  // nodes/signal_gen.rs:111-130: no signal input, two control ports

@@ -625,6 +625,13 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
             core.gr = op.p[1];
             run_recurrence<G>(core, acc, c.tc, c.sm_state + op.aux * G);
         } break;
+        case OP_GATE: {  // extension: hard noise gate keyed by the envelope already in acc
+            float x[kChunk];
+            load16(c.vregs + (op.vreg * kF4) * kThreads + t, kThreads, x);
+            const float thr = op.p[0];
+#pragma unroll
+            for (int i = 0; i < kChunk; i++) acc[i] = acc[i] >= thr ? x[i] : 0.0f;
+        } break;
         case OP_SIGGEN: {  // nodes/signal_gen.rs:55-130: phase accumulates per 128-sample reference block
             float A[kChunk];
             if (op.pflags & 1) load16(c.vregs + (op.pv[0] * kF4) * kThreads + t, kThreads, A);

@@ -50,6 +50,7 @@ enum OpCode : uint8_t {
     OP_HP1,        // z = x*p1 + p0*z ; y = x - z
     OP_ENVELOPE,   // p0 attack gain, p1 release gain, state slot `aux`
     OP_SIGGEN,     // mode; amplitude P0, frequency P1; p2 = sample rate; state slot `aux`
+    OP_GATE,       // EXTENSION (no reference node): acc = acc >= p0 ? V[vreg] : 0   (acc = envelope, vreg = the signal)
 };
 
 // Parameter source flags: bit i set => parameter Pi is a per-sample tile read from vreg pv[i]

@@ -33,6 +33,7 @@ NODE_PORTS: Dict[str, Tuple[Tuple[str, ...], Tuple[str, ...]]] = {
     "demux": (("in",), ("a", "b")),
     "envelope": (("in",), ("out",)),
     "signal_gen": (("amplitude", "frequency"), ("out",)),
+    "gate": (("in",), ("out",)),  # extension: not a reference node (see csrc/engine.cpp kNodeTypes)
     "input": ((), ("out",)),
     "output": (("in",), ()),
 }

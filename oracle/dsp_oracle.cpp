@@ -448,6 +448,30 @@ struct Envelope : Node {
     }
 };
 
+// ---- EXTENSION (no reference node; BASELINE north_star names a noise gate) ----------
+// Hard gate keyed by the Envelope node's detector: out = env(in) >= threshold ? in : 0.
+struct Gate : Node {
+    float threshold = 0.0f, attack = 0.0f, release = 0.0f;
+    std::vector<float> last;
+    Gate() { type = "gate"; in_ports = {"in"}; out_ports = {"out"}; }
+    void reset() override { last.assign(channels, 0.0f); }
+    int set_f32(const std::string& f, float v) override {
+        if (f == "threshold") threshold = v; else if (f == "attack") attack = v; else if (f == "release") release = v; else return E_PORT;
+        return OK;
+    }
+    void process(int ch, const PortIO& io) override {
+        float ga = Envelope::calc_gain(attack), gr = Envelope::calc_gain(release);
+        float prev = last[ch];
+        for (int i = 0; i < REF_BLOCK; i++) {
+            float d = std::fabs(io.in[0][i]);
+            float g = prev < d ? ga : gr;
+            prev = d + (prev - d) * g;
+            io.out[0][i] = prev >= threshold ? io.in[0][i] : 0.0f;
+        }
+        last[ch] = prev;
+    }
+};
+
 // ---- nodes/signal_gen.rs:55-130 ------------------------------------------------------------------
 struct SignalGen : Node {
     enum Mode { Sine, Triangle, Square, Constant };
@@ -513,6 +537,7 @@ std::unique_ptr<Node> make_node(const std::string& t) {  // nodes/mod.rs:92-123 
     if (t == "demux") return std::make_unique<Demux>();
     if (t == "envelope") return std::make_unique<Envelope>();
     if (t == "signal_gen") return std::make_unique<SignalGen>();
+    if (t == "gate") return std::make_unique<Gate>();
     if (t == "input") return std::make_unique<Terminal>(true);
     if (t == "output") return std::make_unique<Terminal>(false);
     return nullptr;

@@ -203,3 +203,30 @@ def test_errors(oracle_mod):
     o.link(1, "out", 0, "in")
     with pytest.raises(oracle_mod.OracleError):
         o.compile()                    # cycle
+
+
+def test_gate_extension_known_answers(oracle_mod):
+    """`gate` is an EXTENSION (BASELINE north_star names a noise gate; the reference has none): hard gate keyed by
+    the Envelope node's detector.  Pinned by hand-derivable answers only."""
+    x = S.noise(2, 256)
+    # default threshold 0.0: the envelope is >= 0 everywhere -> pass-through (two fan-in divisions)
+    y = make_oracle(oracle_mod, single("gate"), 2).process(x)[0]
+    assert_bit_exact(y, (x / NF1) / NF1)
+    # attack = release = 0 frames: gains 0 -> the envelope is |x| itself -> per-sample gate
+    y = make_oracle(oracle_mod, single("gate", threshold=0.2), 2).process(x)[0]
+    xin = x / NF1
+    assert_bit_exact(y, np.where(np.abs(xin) >= f32(0.2), xin, f32(0.0)) / NF1)
+    # a slow release keeps the gate open after a burst: impulse 1.0 then silence, release 100 frames
+    imp = np.zeros((1, 256), dtype=np.float32)
+    imp[0, 0] = 1.0
+    imp[0, 1:] = 1e-3
+    y = make_oracle(oracle_mod, single("gate", threshold=0.5, release=100.0), 1).process(imp)[0]
+    env = float(f32(1.0) / NF1)
+    open_len = 1
+    g = float(np.exp(f32(-1.0) / f32(100.0)))
+    while env * g >= 0.5:   # e^(-k/100) decay: about 69 samples (f64 estimate, checked with a +-2 window)
+        env *= g
+        open_len += 1
+    nz = int(np.count_nonzero(y[0]))
+    assert abs(nz - open_len) <= 2, (nz, open_len)
+    assert np.all(y[0, nz:] == 0.0)
