@@ -17,6 +17,8 @@
 // lane = channel, strictly in time order, on a conflict-free transposed tile in shared memory.
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "exact_math.cuh"
@@ -866,7 +868,7 @@ __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.ar
 
 template <int G, class Core>
 __device__ __forceinline__ void ws_recurrence_warp(Core core, float* tiles, const float4* st_in, float4* st_out, int lane,
-                                                   bool ch_ok, long long n_tiles, long long T) {
+                                                   bool ch_ok, long long n_tiles, long long T, int n_ws) {
     using Q = Geo<G>;  // `lane` is the channel index inside the CTA (or >= G for idle lanes)
     float4 s = make_float4(0, 0, 0, 0);
     if (lane < G && ch_ok) s = *st_in;
@@ -875,14 +877,14 @@ __device__ __forceinline__ void ws_recurrence_warp(Core core, float* tiles, cons
         const int b = (int)(i & 1);
         const long long rem = T - i * Q::S;
         const int valid_f4 = (int)((rem < Q::S ? rem : Q::S) / 4);
-        bar_sync(BAR_FULL0 + b, kWsThreads);
+        bar_sync(BAR_FULL0 + b, n_ws);
         if (lane < G) {
             float4* r = reinterpret_cast<float4*>(tiles + b * (G * Q::ROW) + lane * Q::ROW);
             recurrence_row(core, r, valid_f4);
         }
         __threadfence_block();  // bar.arrive alone orders nothing: make the tile visible first
         __syncwarp();
-        bar_arrive(BAR_DONE0 + b, kWsThreads);
+        bar_arrive(BAR_DONE0 + b, n_ws);
     }
     if (lane < G && ch_ok) {
         core.save(s);
@@ -901,10 +903,13 @@ __device__ __forceinline__ void run_static_range(const Program& prog, const Ctx<
 
 template <int G, class Chain>
 __global__ void __launch_bounds__(kWsLaunchThreads, 2)
-fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, long long T, int n_sm, int rec_index) {
+fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, long long T, int gc, int rec_index) {
+    // gc <= G: channels this CTA really owns.  The launcher trims gc so that the grid is ONE balanced wave (every SM
+    // gets the same number of channels); the CTA is launched with only gc * TPC elementwise threads + the R warp.
+    const int n_e = gc * Geo<G>::TPC, n_ws = n_e + 32 * kNR;
     using Q = Geo<G>;
     extern __shared__ float4 smem4[];
-    const int t = threadIdx.x;  // t < kThreads: elementwise thread, else R-warp thread
+    const int t = threadIdx.x;  // t < n_e: elementwise thread, else R-warp thread
     // shared memory: [G] x-state (float2) | edge[256] | tiles[2][G*ROW] | stage
     float2* xstate = reinterpret_cast<float2*>(smem4);
     float2* edge = xstate + 64;  // xstate[2][32]: read parity i & 1, written parity (i + 1) & 1
@@ -914,13 +919,12 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
     const Op& rop = prog.ops[rec_index];
     const int rcode = Chain::n > 0 ? (Chain::sig(Chain::rec) & 0xff) : rop.code;
     float* stp = prog.states[rop.aux];
-    (void)n_sm;
 
-    if (t >= kThreads) {  // ---------------- R warps ----------------
+    if (t >= n_e) {  // ---------------- R warps ----------------
         constexpr int GP = (G + kNR - 1) / kNR;  // channels per R warp
-        const int rw = (t - kThreads) >> 5, rl = t & 31;
-        const int lane = rl < GP ? rw * GP + rl : G;  // channel inside the CTA; G = idle lane
-        const int ch = c_begin + blockIdx.x * G + lane;
+        const int rw = (t - n_e) >> 5, rl = t & 31;
+        const int lane = (rl < GP && rw * GP + rl < gc) ? rw * GP + rl : G;  // channel inside the CTA; G = idle lane
+        const int ch = c_begin + blockIdx.x * gc + lane;
         const bool ok = lane < G && ch < c_end;
         const float4* sin = reinterpret_cast<const float4*>(stp) + (ok ? ch : 0);
         float4* sout = reinterpret_cast<float4*>(stp) + (ok ? ch : 0);
@@ -938,7 +942,7 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
 #ifdef DSPB_WS_TIMING
                 long long tq0 = clock64();
 #endif
-                bar_sync(BAR_FULL0 + b, kWsThreads);
+                bar_sync(BAR_FULL0 + b, n_ws);
 #ifdef DSPB_WS_TIMING
                 long long tq1 = clock64();
 #endif
@@ -947,19 +951,19 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
                     recurrence_row(core, r, valid_f4);
                 }
 #ifdef DSPB_WS_TIMING
-                if (blockIdx.x == 0 && t == kThreads) { long long tq2 = clock64(); g_ws_timing[0] += tq1 - tq0; g_ws_timing[1] += tq2 - tq1; }
+                if (blockIdx.x == 0 && t == n_e) { long long tq2 = clock64(); g_ws_timing[0] += tq1 - tq0; g_ws_timing[1] += tq2 - tq1; }
 #endif
                 __threadfence_block();
                 __syncwarp();
-                bar_arrive(BAR_DONE0 + b, kWsThreads);
+                bar_arrive(BAR_DONE0 + b, n_ws);
             }
             if (ok) { float* f = reinterpret_cast<float*>(sout); f[2] = core.y1; f[3] = core.y2; }
         } else if (rcode == OP_LP1) {
             OnePoleCore core; core.r = rop.p[0];
-            ws_recurrence_warp<G>(core, tiles, sin, sout, lane, ok, n_tiles, T);
+            ws_recurrence_warp<G>(core, tiles, sin, sout, lane, ok, n_tiles, T, n_ws);
         } else {
             EnvCore core; core.ga = rop.p[0]; core.gr = rop.p[1];
-            ws_recurrence_warp<G>(core, tiles, sin, sout, lane, ok, n_tiles, T);
+            ws_recurrence_warp<G>(core, tiles, sin, sout, lane, ok, n_tiles, T, n_ws);
         }
         return;
     }
@@ -970,7 +974,7 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
     c.t = t;
     c.g = t / Q::TPC;
     c.j = t % Q::TPC;
-    c.ch = c_begin + blockIdx.x * G + c.g;
+    c.ch = c_begin + blockIdx.x * gc + c.g;
     c.ch_ok = c.ch < c_end;
     c.T = (int)T;
     c.init_streams(prog);
@@ -983,16 +987,21 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
     c.tc.g = c.g;
     c.tc.j = c.j;
     c.tc.rec_warp = 8;
-    if (t < G) {
-        const int ch = c_begin + blockIdx.x * G + t;
+    if (t < gc) {
+        const int ch = c_begin + blockIdx.x * gc + t;
         xstate[t] = (rcode == OP_BIQUAD && ch < c_end) ? *reinterpret_cast<const float2*>(stp + 4 * (long long)ch) : make_float2(0.f, 0.f);
+    }
+    float cx1 = 0.0f, cx2 = 0.0f;  // biquad x1, x2 carried from tile to tile (TPC <= 32: every lane of the channel holds them)
+    if (Q::TPC <= 32 && rcode == OP_BIQUAD && c.ch_ok) {
+        const float2 s2 = *reinterpret_cast<const float2*>(stp + 4 * (long long)c.ch);
+        cx1 = s2.x; cx2 = s2.y;
     }
     Pf pf;
 #pragma unroll
     for (int i = 0; i < kChunk; i++) pf.in[i] = pf.ring[i] = 0.0f;
     if (prog.pf_buf[0] >= 0) c.prefetch_in(0, pf.in);
     if (prog.pf_ring[1] >= 0) c.prefetch_ring(c.ring_slot, c.j * kChunk, pf.ring);
-    bar_sync(BAR_EONLY, kThreads);
+    bar_sync(BAR_EONLY, n_e);
 
     auto set_tile = [&](int ti) {
         c.tile_i = ti;
@@ -1011,7 +1020,7 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
 #endif
         // edge[] is rewritten below: from i = 2 on, the BAR_DONE sync of the previous iteration already orders
         // that behind every thread's reads (and the ring stores of tile i-2 before the loads of tile i-1)
-        if (i <= 1) bar_sync(BAR_EONLY, kThreads);
+        if (i <= 1) bar_sync(BAR_EONLY, n_e);
 #ifdef DSPB_WS_TIMING
         if (blockIdx.x == 0 && t == 0) g_ws_timing[5] += clock64() - tb0;
 #endif
@@ -1039,15 +1048,26 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
             if (rpre & 2) div16(acc, ConstDiv{rop.p[4], rop.p[5]}, rpre & 4);
             if (rcode == OP_BIQUAD) {
                 const float b0 = rop.p[0], b1 = rop.p[1], b2 = rop.p[2];
-                edge[t] = make_float2(acc[kChunk - 2], acc[kChunk - 1]);
-                bar_sync(BAR_EONLY, kThreads);
+                const float nx1 = acc[kChunk - 1], nx2 = acc[kChunk - 2];
+                float xm1, xm2;
+                if constexpr (Q::TPC <= 32) {
+                    // a channel's threads sit in one warp: the two samples before this chunk come from the lane
+                    // below by shuffle, the tile-to-tile carry (x1, x2 of the DF1 state) stays in registers --
+                    // no shared-memory exchange and no CTA-wide barrier on the elementwise warps' path
+                    xm1 = __shfl_up_sync(0xffffffffu, nx1, 1, Q::TPC);
+                    xm2 = __shfl_up_sync(0xffffffffu, nx2, 1, Q::TPC);
+                    if (c.j == 0) { xm1 = cx1; xm2 = cx2; }
+                    cx1 = __shfl_sync(0xffffffffu, nx1, c.j_last, Q::TPC);
+                    cx2 = __shfl_sync(0xffffffffu, nx2, c.j_last, Q::TPC);
+                } else {
+                    edge[t] = make_float2(acc[kChunk - 2], acc[kChunk - 1]);
+                    bar_sync(BAR_EONLY, n_e);
+                    if (c.j == 0) { const float2 s2 = xstate[(i & 1) * 32 + c.g]; xm1 = s2.x; xm2 = s2.y; }
+                    else { const float2 e = edge[t - 1]; xm2 = e.x; xm1 = e.y; }
+                }
 #ifdef DSPB_WS_TIMING
                 tp2 = clock64();
 #endif
-                float xm1, xm2;
-                if (c.j == 0) { const float2 s2 = xstate[(i & 1) * 32 + c.g]; xm1 = s2.x; xm2 = s2.y; }
-                else { const float2 e = edge[t - 1]; xm2 = e.x; xm1 = e.y; }
-                const float nx1 = acc[kChunk - 1], nx2 = acc[kChunk - 2];
                 float pm1 = acc[0], pm2;
                 acc[0] = add(add(mul(b0, acc[0]), mul(b1, xm1)), mul(b2, xm2));
                 pm2 = pm1; pm1 = acc[1];
@@ -1058,7 +1078,9 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
                     acc[k] = add(add(mul(b0, xi), mul(b1, pm1)), mul(b2, pm2));
                     pm2 = pm1; pm1 = xi;
                 }
-                if (c.j == c.j_last) xstate[((i + 1) & 1) * 32 + c.g] = make_float2(nx1, nx2);
+                if constexpr (Q::TPC > 32) {
+                    if (c.j == c.j_last) xstate[((i + 1) & 1) * 32 + c.g] = make_float2(nx1, nx2);
+                }
             } else if (rcode == OP_LP1) {
                 const float omr = rop.p[1];
 #pragma unroll
@@ -1072,14 +1094,14 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
             for (int k = 0; k < kF4; k++)
                 row[kF4 * c.j + (k ^ sw_of(c.j))] = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
             __threadfence_block();
-            bar_arrive(BAR_FULL0 + (int)(i & 1), kWsThreads);
+            bar_arrive(BAR_FULL0 + (int)(i & 1), n_ws);
         }
 #ifdef DSPB_WS_TIMING
         te1 = clock64();
 #endif
         if (i >= 1) {  // ---- ops after the recurrence, tile i-1 ----
             const int b = (int)((i - 1) & 1);
-            bar_sync(BAR_DONE0 + b, kWsThreads);
+            bar_sync(BAR_DONE0 + b, n_ws);
 #ifdef DSPB_WS_TIMING
             te2 = clock64();
 #endif
@@ -1099,9 +1121,11 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
             if (tp1) { g_ws_timing[6] += tp1 - te0; g_ws_timing[7] += tp2 - tp1; } }
 #endif
     }
-    bar_sync(BAR_EONLY, kThreads);
-    if (rcode == OP_BIQUAD && t < G) {
-        const int ch = c_begin + blockIdx.x * G + t;
+    bar_sync(BAR_EONLY, n_e);
+    if constexpr (Q::TPC <= 32) {
+        if (rcode == OP_BIQUAD && c.j == 0 && c.ch_ok) *reinterpret_cast<float2*>(stp + 4 * (long long)c.ch) = make_float2(cx1, cx2);
+    } else if (rcode == OP_BIQUAD && t < gc) {
+        const int ch = c_begin + blockIdx.x * gc + t;
         if (ch < c_end) *reinterpret_cast<float2*>(stp + 4 * (long long)ch) = xstate[(nt & 1) * 32 + t];
     }
 }
@@ -1140,13 +1164,41 @@ template <int G, class Chain>
 int launch_ws(const Program& prog, int c_begin, int c_end, int64_t T, int rec_index, cudaStream_t st) {
     const int smem = ws_smem_bytes(prog, G);
     static int configured = -1;
+    static int regs = 0, n_sm = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(fused_kernel_ws<G, Chain>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         configured = smem;
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, fused_kernel_ws<G, Chain>) == cudaSuccess) regs = fa.numRegs;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        if (n_sm <= 0) n_sm = 148;
     }
-    const int n_cta = (c_end - c_begin + G - 1) / G;
-    fused_kernel_ws<G, Chain><<<n_cta, kWsLaunchThreads, smem, st>>>(prog, c_begin, c_end, (long long)T, 148, rec_index);
+    // Channels per CTA: G, or a smaller power of two when a channel is one warp (TPC == 32): smaller CTAs (8 channels
+    // = 9 warps, 4 resident per SM) balance better and measured 0.344 ms against 0.368 ms for the config-3 chain at
+    // 4096 channels.  The grid has to stay ONE wave, and the capacity that counts is not n_sm x CTAs-per-SM:
+    // measured on B200 (DSPB_GC sweep, profiles/r01s3_fused_gc_sweep.txt), CTAs are dealt evenly to the 8 GPCs
+    // and the smallest GPC has 16 SMs, so a grid runs in one wave only while n_cta / 8 <= 16 x CTAs-per-SM.
+    // 293 CTAs of 14 channels (a "perfectly balanced" 2 per SM on paper) took 2.1x as long: the CTAs that did not
+    // fit their GPC started when the first ones had finished (ncu: sm__cycles_active min 437 K / max 1506 K).
+    int gc = G;
+    static const bool no_balance = getenv("DSPB_NO_BALANCE") != nullptr;
+    if (Geo<G>::TPC == 32 && regs > 0 && !no_balance) {
+        const int n = c_end - c_begin;
+        for (int g = G / 2; g >= 8; g >>= 1) {
+            const int warps = g + kNR;
+            const int cps = std::min(65536 / (regs * 32 * warps), (227 * 1024) / (smem + 1024));
+            const int n_cta = (n + g - 1) / g;
+            if (cps >= 1 && (n_cta + 7) / 8 <= 16 * cps) gc = g;
+        }
+    }
+    if (const char* f = getenv("DSPB_GC")) { const int v = atoi(f); if (v >= 1 && v <= G && Geo<G>::TPC == 32) gc = v; }
+    const int n_cta = (c_end - c_begin + gc - 1) / gc;
+    static bool said = false;
+    if (!said && getenv("DSPB_DEBUG")) { fprintf(stderr, "[dspb] fused_kernel_ws: G=%d gc=%d n_cta=%d regs=%d smem=%d\n", G, gc, n_cta, regs, smem); said = true; }
+    fused_kernel_ws<G, Chain><<<n_cta, gc * Geo<G>::TPC + 32 * kNR, smem, st>>>(prog, c_begin, c_end, (long long)T, gc, rec_index);
     return (int)cudaGetLastError();
 }
 
