@@ -1333,6 +1333,41 @@ int dspb_process(dspb_engine* e, const float* const* inputs, float* const* outpu
     return DSPB_OK;
 }
 
+// ---- device-boundary format steps (boundary.cu) ----------------------------------------------------------
+static int boundary_step(dspb_engine* e, const float* src, float* dst, int64_t n_frames, int mem_kind, void* stream, bool fold) {
+    if (!e || (n_frames > 0 && (!src || !dst))) return fail(DSPB_ERR_INVALID, "null argument");
+    if (n_frames < 0) return fail(DSPB_ERR_INVALID, "n_frames must be >= 0");
+    if (e->plan_only) return fail(DSPB_ERR_CUDA, "engine was created with device = -1 (planning only): no CUDA device, no CPU fallback");
+    if (n_frames == 0) return DSPB_OK;
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    const long long total = (long long)e->cfg.channels * n_frames;
+    const size_t in_bytes = (size_t)total * (fold ? 8 : 4), out_bytes = (size_t)total * (fold ? 4 : 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mem_kind == DSPB_MEM_DEVICE) {
+        int rc = fold ? dspb::launch_fold_stereo(src, dst, total, st) : dspb::launch_dup_stereo(src, dst, total, st);
+        if (rc) return fail(DSPB_ERR_CUDA, "boundary kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+        return DSPB_OK;
+    }
+    if (mem_kind != DSPB_MEM_HOST) return fail(DSPB_ERR_INVALID, "mem_kind must be DSPB_MEM_DEVICE or DSPB_MEM_HOST");
+    float *din = nullptr, *dout = nullptr;
+    CUDA_TRY(cudaMallocAsync(&din, in_bytes, st));
+    CUDA_TRY(cudaMallocAsync(&dout, out_bytes, st));
+    CUDA_TRY(cudaMemcpyAsync(din, src, in_bytes, cudaMemcpyHostToDevice, st));
+    int rc = fold ? dspb::launch_fold_stereo(din, dout, total, st) : dspb::launch_dup_stereo(din, dout, total, st);
+    if (rc) return fail(DSPB_ERR_CUDA, "boundary kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+    CUDA_TRY(cudaMemcpyAsync(dst, dout, out_bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaFreeAsync(din, st));
+    CUDA_TRY(cudaFreeAsync(dout, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return DSPB_OK;
+}
+int dspb_fold_stereo(dspb_engine* e, const float* interleaved, float* mono, int64_t n_frames, int mem_kind, void* cuda_stream) {
+    return boundary_step(e, interleaved, mono, n_frames, mem_kind, cuda_stream, true);
+}
+int dspb_dup_stereo(dspb_engine* e, const float* mono, float* interleaved, int64_t n_frames, int mem_kind, void* cuda_stream) {
+    return boundary_step(e, mono, interleaved, n_frames, mem_kind, cuda_stream, false);
+}
+
 int dspb_node_get_i64(dspb_engine* e, int64_t node_id, const char* key, int64_t* out) {
     if (!e || !key || !out) return fail(DSPB_ERR_INVALID, "null argument");
     if (!strcmp(key, "kernel_launches")) { *out = e->last_launches; return DSPB_OK; }

@@ -129,6 +129,9 @@ int launch_fir(const FirPlan& fp, const float* U, int64_t u_stride, float* Y, in
 // Computes H from the (device-resident, reversed, f64) taps with the kernel's own forward passes in f64.
 int fir_prepare_spectrum(int log2F, const double* taps_rev_dev, int n_taps, float2* H_dev, void* stream);
 int fir_fft_max_taps();
+// device-boundary format steps (boundary.cu): stereo fold a + b, mono -> stereo duplicate; flat [C * n] streams
+int launch_fold_stereo(const float* interleaved, float* mono, long long total_mono, cudaStream_t st);
+int launch_dup_stereo(const float* mono, float* interleaved, long long total_mono, cudaStream_t st);
 // Toeplitz tensor-core path (fir_toeplitz.cu): buffer sizes, tile construction for one tap set
 int fir_toeplitz_max_taps();
 size_t fir_toeplitz_tiles_bytes(int n_taps);

@@ -53,6 +53,7 @@ ABI_SYMBOLS = [
     "dspb_node_set_f32", "dspb_node_set_enum", "dspb_node_set_taps", "dspb_node_set_impulse_response", "dspb_link",
     "dspb_load_graph_json", "dspb_compile", "dspb_process", "dspb_node_process", "dspb_reset_state",
     "dspb_node_get_i64", "dspb_node_port_index", "dspb_describe_plan", "dspb_profile_enable", "dspb_profile_read",
+    "dspb_fold_stereo", "dspb_dup_stereo",
 ]
 
 _lib = None
@@ -88,6 +89,8 @@ def load_library(path: Optional[str] = None):
     L.dspb_profile_enable.argtypes = [vp, ctypes.c_int]
     L.dspb_profile_read.argtypes = [vp, vp, vp, ctypes.c_int]
     L.dspb_describe_plan.argtypes = [vp, vp, i64]
+    L.dspb_fold_stereo.argtypes = [vp, vp, vp, i64, ctypes.c_int, vp]
+    L.dspb_dup_stereo.argtypes = [vp, vp, vp, i64, ctypes.c_int, vp]
     L.dspb_describe_plan.restype = i64
     if path is None:
         _lib = L
@@ -240,6 +243,23 @@ class Engine:
         ip = (ctypes.c_void_p * max(1, len(inputs)))(*[ptr(t) for t in inputs])
         op = (ctypes.c_void_p * max(1, len(outputs)))(*[ptr(t) for t in outputs])
         self._ck(self._L.dspb_process(self._h, ip, op, n_samples, MEM_HOST, None))
+
+    # ---- device-boundary format steps (devices.rs:244-262, 443-500) ---------------------------------------
+    def fold_stereo(self, interleaved: np.ndarray) -> np.ndarray:
+        """[C, n_frames, 2] interleaved stereo -> [C, n_frames] mono, a + b (host buffers)."""
+        x = np.ascontiguousarray(interleaved, dtype=np.float32)
+        assert x.ndim == 3 and x.shape[0] == self.channels and x.shape[2] == 2
+        out = np.empty(x.shape[:2], dtype=np.float32)
+        self._ck(self._L.dspb_fold_stereo(self._h, x.ctypes.data, out.ctypes.data, x.shape[1], MEM_HOST, None))
+        return out
+
+    def dup_stereo(self, mono: np.ndarray) -> np.ndarray:
+        """[C, n_frames] mono -> [C, n_frames, 2] interleaved stereo, both slots = the mono sample (host buffers)."""
+        x = np.ascontiguousarray(mono, dtype=np.float32)
+        assert x.ndim == 2 and x.shape[0] == self.channels
+        out = np.empty(x.shape + (2,), dtype=np.float32)
+        self._ck(self._L.dspb_dup_stereo(self._h, x.ctypes.data, out.ctypes.data, x.shape[1], MEM_HOST, None))
+        return out
 
     def process(self, inputs, n_samples: Optional[int] = None) -> List[np.ndarray]:
         """Convenience for tests: numpy in, numpy out, through the host-buffer path."""

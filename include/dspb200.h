@@ -138,6 +138,16 @@ int dspb_node_process(dspb_engine* e, int64_t node_id, const float* const* port_
                       const uint8_t* present, float* const* port_outputs, int64_t n_samples,
                       int mem_kind, void* cuda_stream);
 
+/* ---- device-boundary format steps ---------------------------------------- */
+
+/* Replaces: the stereo fold of the capture callback, devices.rs:244-262 `do_read_2`: interleaved frames
+ * [C x n_frames x 2] -> mono [C x n_frames], out = a + b (f32 add, not an average).  Any n_frames >= 0. */
+int dspb_fold_stereo(dspb_engine* e, const float* interleaved, float* mono, int64_t n_frames, int mem_kind, void* cuda_stream);
+/* Replaces: the mono -> stereo duplicate of the playback callback, devices.rs:443-500 `do_write_2`
+ * (`o.fill(x)`): mono [C x n_frames] -> interleaved [C x n_frames x 2].  The 48 kHz -> device-rate sinc resampler
+ * in front of it (dasp Sinc<[f32;16]>, un-vendored) is not part of this library: streams stay at 48 kHz. */
+int dspb_dup_stereo(dspb_engine* e, const float* mono, float* interleaved, int64_t n_frames, int mem_kind, void* cuda_stream);
+
 /* Clears all per-channel state (what a fresh NodeStatic::new / restore gives). */
 int dspb_reset_state(dspb_engine* e);
 
