@@ -69,6 +69,17 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_tensor_peak():
+    """Dense bf16 TFLOP/s: the sustained figure (a kernel timed inside a long step), else the recipe's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["bf16_tflops_sustained"]), "measured sustained (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 1590.0, "fallback (B200_PROFILING.md)"
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
 
@@ -319,6 +330,16 @@ def main():
             "gpu_launches": int(launches_per_step * args.steps),
             "clocks": clocks,
         }
+        if args.fir_mode == 2 and dom["kind"] == "fir":
+            # Toeplitz tensor-core FIR: the bounding roofline is the tensor pipe.  Algorithmic flops of the kernel =
+            # 3 split-bf16 products x 2 N flop per channel-sample (N taps), all launches of the step (split pre-pass included)
+            n_taps = max([len(nd.taps) for nd in spec.nodes if nd.typename == "fir" and nd.taps is not None] or [1])
+            tf = 3 * 2 * n_taps * C * n / (dom["avg_ms"] * 1e-3) / 1e12
+            tpeak, tsrc = load_tensor_peak()
+            line["roofline"].update({"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                                     "peak_source": tsrc, "traffic": None,
+                                     "flops_per_channel_sample": 3 * 2 * n_taps,
+                                     "hbm_view": {"achieved_gbs": achieved, "peak_gbs": peak}})
         if not args.no_e2e:
             line["e2e"] = {"value": float(world) * C * n * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                            "h2d_bytes_per_step": n_in * C * n * 4, "d2h_bytes_per_step": n_out * C * n * 4}

@@ -66,3 +66,27 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cpp", ".cu", ".h")):
                 text = open(os.path.join(dp, f), errors="replace").read()
                 assert "liboracle" not in text and "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_planning_mode_describes_every_fir_kernel_and_extension_node(lib):
+    """device = -1 builds schedules without a GPU (and refuses to process): the host scheduler is CPU-testable."""
+    from dsp_stuff_b200 import GraphSpec
+    from dsp_stuff_b200 import signals as S
+    from dsp_stuff_b200.engine import Engine, EngineError
+
+    want = {0: "overlap-save FFT 2^13,", 1: "direct f64 sum", 2: "Toeplitz-tiled tcgen05 GEMM", 3: "packed f32x2 variant"}
+    for mode, text in want.items():
+        e = Engine(4096, block=1024, max_samples=16384, device=-1, fir_mode=mode)
+        S.target_chain(4096).apply(e)
+        plan = e.describe_plan()
+        assert text in plan, (mode, plan[-300:])
+        assert "fused segment: G=16" in plan
+    with pytest.raises(EngineError):
+        Engine(4, device=-1, fir_mode=7)
+    # the gate extension lowers to save -> envelope -> select
+    g = (GraphSpec().node(10, "input").node(11, "output").node(0, "gate", threshold=0.25, release=50.0)
+         .link(10, "out", 0, "in").link(0, "out", 11, "in"))
+    e = Engine(64, device=-1)
+    g.apply(e)
+    plan = e.describe_plan()
+    assert "envelope(" in plan and "(extension)" in plan
