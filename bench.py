@@ -53,7 +53,7 @@ def parse_args():
 # (workload, kind, channels, samples per step) -> bytes
 TRAFFIC = {
     ("target", "fir", 4096, 16384): 335779840 + 229628672,     # profiles/r01s3_target_fir_fft_kernel.txt
-    ("target", "fused", 4096, 16384): 539016192 + 484716032,   # profiles/r01s3_target_fused_chain_kernel.txt
+    ("target", "fused", 4096, 16384): 539587328 + 487191552,   # profiles/r01s4_target_fused_chain_kernel.txt
 }
 
 DEFAULT_CHANNELS = {"config1": 2, "config2": 256, "config3": 1024, "config4": 4096, "config5": 1024, "target": 4096}
