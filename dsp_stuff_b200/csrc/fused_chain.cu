@@ -981,7 +981,7 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
     c.sm_state = nullptr;
     c.edge = edge;
     c.stage = stage;
-    c.vregs = nullptr;
+    c.vregs = stage;  // [n_vregs][kF4][kThreads]; none of them is live across the recurrence (ws_rec_index)
     c.n_tiles = (int)n_tiles;
     c.tc.tile = tiles;
     c.tc.g = c.g;
@@ -1142,12 +1142,21 @@ int ws_timing_read(long long* out, bool clear) {
 namespace {
 int ws_smem_bytes(const Program& prog, int G) {
     const int S = kTile / G;
-    (void)prog;
-    return 64 * 8 + kThreads * 8 + 2 * G * (S + 4) * 4;
+    return 64 * 8 + kThreads * 8 + 2 * G * (S + 4) * 4 + prog.n_vregs * kTile * 4;
 }
-// index of the single recurrence op if the program qualifies for the warp-specialised kernel, else -1
+// does op read / write shared-memory vreg v?
+bool op_reads_vreg(const Op& op, int v) {
+    const int c = op.code;
+    if ((c == OP_LOADV || c == OP_ADDV || c == OP_COPYV || c == OP_ADD || c == OP_MIX || c == OP_GATE) && op.vreg == v) return true;
+    for (int i = 0; i < 3; i++)
+        if ((op.pflags & (1 << i)) && op.pv[i] == v) return true;
+    return false;
+}
+// index of the single recurrence op if the program qualifies for the warp-specialised kernel, else -1.
+// Shared-memory vregs are fine as long as none is live ACROSS the recurrence: the elementwise warps run the ops
+// before it for tile i and the ops after it for tile i-1 in the same iteration, so a value saved before and read
+// after would be overwritten by the next tile in between.
 int ws_rec_index(const Program& p) {
-    if (p.n_vregs != 0) return -1;
     int idx = -1;
     for (int i = 0; i < p.n_ops; i++) {
         const int c = p.ops[i].code;
@@ -1156,6 +1165,17 @@ int ws_rec_index(const Program& p) {
             idx = i;
         }
         if (c == OP_HP1 || c == OP_SIGGEN) return -1;
+    }
+    if (idx < 0) return -1;
+    for (int v = 0; v < p.n_vregs; v++) {
+        bool before = false, after = false;
+        for (int i = 0; i < p.n_ops; i++) {
+            const bool touches = op_reads_vreg(p.ops[i], v) || (p.ops[i].code == OP_SAVEV && p.ops[i].vreg == v);
+            if (touches && i < idx) before = true;
+            if (touches && i > idx) after = true;
+        }
+        if (op_reads_vreg(p.ops[idx], v)) return -1;  // a control-port tile feeding the recurrence op itself
+        if (before && after) return -1;
     }
     return idx;
 }
