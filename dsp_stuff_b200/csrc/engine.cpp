@@ -526,8 +526,17 @@ void Lowerer::close_fused() {
     const int C = e.cfg.channels;
     int G = 1;
     if (has_rec) {
-        G = 32;
-        while (G > 1 && (C + G - 1) / G < 256) G >>= 1;
+        if (C <= 2048 && P.n_vregs == 0 && P.n_ops <= 8) {
+            // few channels per SM and a light chain: the kernel is bound by the sequential recurrence chain, not by
+            // elementwise work (measured: heavier graphs such as config 5's 17-op segment with shared-memory vregs are
+            // better off with 256 CTAs at two per SM).
+            // One CTA per SM in one wave (<= 8 GPCs x 16 SMs = 128 CTAs) lets the warp-specialised kernel give the
+            // recurrence warp an SM sub-partition of its own (fused_chain.cu, XR layout: 14 instead of ~35 cycles per step).
+            while (G < 32 && (C + G - 1) / G > 128) G <<= 1;
+        } else {
+            G = 32;
+            while (G > 1 && (C + G - 1) / G < 256) G >>= 1;
+        }
     }
     while ((int64_t)kTile / G > min_ring && G < 32) G <<= 1;
     if (e.force_G) G = e.force_G;

@@ -901,15 +901,33 @@ __device__ __forceinline__ void run_static_range(const Program& prog, const Ctx<
     }
 }
 
-template <int G, class Chain>
-__global__ void __launch_bounds__(kWsLaunchThreads, 2)
+// XR ("exclusive R"): the recurrence warp gets an SM sub-partition of its own.  Warp w of a CTA issues on
+// sub-partition w % 4; measured (tests/cuda/rec_microbench.cu) the lane = channel feedback loop takes 14.2 cycles per
+// sample alone or next to FP work on the OTHER sub-partitions, but 39.6 cycles as soon as two busy warps share its
+// scheduler.  In the XR layout physical warp 3 is the R warp, warps 7, 11, ... exit at once and the elementwise
+// threads are renumbered over the remaining warps; the CTA is launched with 24 warps (a multiple of 4 keeps the
+// mapping aligned for a co-resident CTA).  The elementwise warps lose a quarter of the issue slots, so the
+// launcher uses XR only when the recurrence chain, not the elementwise work, bounds the kernel (few channels per SM).
+constexpr int kXrLaunchThreads = 768;
+template <int G, class Chain, bool XR>
+__global__ void __launch_bounds__(XR ? kXrLaunchThreads : kWsLaunchThreads, XR ? 1 : 2)
 fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, long long T, int gc, int rec_index) {
     // gc <= G: channels this CTA really owns.  The launcher trims gc so that the grid is ONE balanced wave (every SM
     // gets the same number of channels); the CTA is launched with only gc * TPC elementwise threads + the R warp.
     const int n_e = gc * Geo<G>::TPC, n_ws = n_e + 32 * kNR;
     using Q = Geo<G>;
     extern __shared__ float4 smem4[];
-    const int t = threadIdx.x;  // t < n_e: elementwise thread, else R-warp thread
+    int t = threadIdx.x;  // logical index; t < n_e: elementwise thread, else R-warp thread
+    if constexpr (XR) {
+        const int pw = t >> 5;
+        if ((pw & 3) == 3) {
+            if (pw != 3) return;
+            t = n_e + (t & 31);
+        } else {
+            t = (pw - (pw >> 2)) * 32 + (t & 31);
+            if (t >= n_e) return;
+        }
+    }
     // shared memory: [G] x-state (float2) | edge[256] | tiles[2][G*ROW] | stage
     float2* xstate = reinterpret_cast<float2*>(smem4);
     float2* edge = xstate + 64;  // xstate[2][32]: read parity i & 1, written parity (i + 1) & 1
@@ -1180,21 +1198,28 @@ int ws_rec_index(const Program& p) {
     return idx;
 }
 
-template <int G, class Chain>
+template <int G, class Chain, bool XR>
 int launch_ws(const Program& prog, int c_begin, int c_end, int64_t T, int rec_index, cudaStream_t st) {
     const int smem = ws_smem_bytes(prog, G);
     static int configured = -1;
     static int regs = 0, n_sm = 0;
     if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(fused_kernel_ws<G, Chain>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaError_t e = cudaFuncSetAttribute(fused_kernel_ws<G, Chain, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
         configured = smem;
         cudaFuncAttributes fa;
-        if (cudaFuncGetAttributes(&fa, fused_kernel_ws<G, Chain>) == cudaSuccess) regs = fa.numRegs;
+        if (cudaFuncGetAttributes(&fa, fused_kernel_ws<G, Chain, XR>) == cudaSuccess) regs = fa.numRegs;
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         if (n_sm <= 0) n_sm = 148;
+    }
+    if (XR) {
+        const int n_cta = (c_end - c_begin + G - 1) / G;
+        static bool said = false;
+        if (!said && getenv("DSPB_DEBUG")) { fprintf(stderr, "[dspb] fused_kernel_ws XR: G=%d n_cta=%d regs=%d smem=%d\n", G, n_cta, regs, smem); said = true; }
+        fused_kernel_ws<G, Chain, true><<<n_cta, kXrLaunchThreads, smem, st>>>(prog, c_begin, c_end, (long long)T, G, rec_index);
+        return (int)cudaGetLastError();
     }
     // Channels per CTA: G, or a smaller power of two when a channel is one warp (TPC == 32): smaller CTAs (8 channels
     // = 9 warps, 4 resident per SM) balance better and measured 0.344 ms against 0.368 ms for the config-3 chain at
@@ -1218,7 +1243,7 @@ int launch_ws(const Program& prog, int c_begin, int c_end, int64_t T, int rec_in
     const int n_cta = (c_end - c_begin + gc - 1) / gc;
     static bool said = false;
     if (!said && getenv("DSPB_DEBUG")) { fprintf(stderr, "[dspb] fused_kernel_ws: G=%d gc=%d n_cta=%d regs=%d smem=%d\n", G, gc, n_cta, regs, smem); said = true; }
-    fused_kernel_ws<G, Chain><<<n_cta, gc * Geo<G>::TPC + 32 * kNR, smem, st>>>(prog, c_begin, c_end, (long long)T, gc, rec_index);
+    fused_kernel_ws<G, Chain, false><<<n_cta, gc * Geo<G>::TPC + 32 * kNR, smem, st>>>(prog, c_begin, c_end, (long long)T, gc, rec_index);
     return (int)cudaGetLastError();
 }
 
@@ -1264,9 +1289,17 @@ int launch_g(const Program& prog, int c_begin, int c_end, int64_t T, int n_state
     static const bool no_ws = getenv("DSPB_NO_WS") != nullptr;
     const int rec = (G <= 32 && !no_ws) ? ws_rec_index(prog) : -1;
     if (rec >= 0 && ws_smem_bytes(prog, G) <= 200 * 1024) {
-        if (!no_static && chain_matches<ChainGDBR<3>>(prog)) return launch_ws<G, ChainGDBR<3>>(prog, c_begin, c_end, T, rec, st);
-        if (!no_static && chain_matches<ChainGDBR<1>>(prog)) return launch_ws<G, ChainGDBR<1>>(prog, c_begin, c_end, T, rec, st);
-        return launch_ws<G, ChainDynamic>(prog, c_begin, c_end, T, rec, st);
+        // chain-bound launches (at most one CTA per SM and one wave: n_cta <= 8 GPCs x 16 SMs) give the recurrence
+        // warp a sub-partition of its own
+        static const bool no_xr = getenv("DSPB_NO_XR") != nullptr;
+        const bool xr = !no_xr && (c_end - c_begin + G - 1) / G <= 128 && prog.n_vregs == 0 && prog.n_ops <= 8;
+        if (xr) {
+            if (!no_static && chain_matches<ChainGDBR<3>>(prog)) return launch_ws<G, ChainGDBR<3>, true>(prog, c_begin, c_end, T, rec, st);
+            return launch_ws<G, ChainDynamic, true>(prog, c_begin, c_end, T, rec, st);
+        }
+        if (!no_static && chain_matches<ChainGDBR<3>>(prog)) return launch_ws<G, ChainGDBR<3>, false>(prog, c_begin, c_end, T, rec, st);
+        if (!no_static && chain_matches<ChainGDBR<1>>(prog)) return launch_ws<G, ChainGDBR<1>, false>(prog, c_begin, c_end, T, rec, st);
+        return launch_ws<G, ChainDynamic, false>(prog, c_begin, c_end, T, rec, st);
     }
     if (!no_static) {
         if (chain_matches<ChainGDBR<3>>(prog)) return launch_gc<G, ChainGDBR<3>>(prog, c_begin, c_end, T, n_states, st);
