@@ -1148,6 +1148,279 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
     }
 }
 
+
+// ======================= two recurrences in series, pipelined over two recurrence warps =======================
+// BASELINE config 2 (biquad low-pass -> biquad high-pass) is nothing but two sequential feedback chains: run back to
+// back they cost ~2 x 15 cycles per sample.  Here recurrence warp R1 works on tile i while R2 works on tile i-1 and
+// the elementwise warps feed both: iteration i runs the ops before recurrence 1 for tile i, the ops between the two
+// for tile i-1 and the ops after recurrence 2 for tile i-2.  Same hand-off protocol as fused_kernel_ws (named
+// barriers FULL / DONE per stage and tile parity), same XR layout (R1 = physical warp 3, R2 = warp 7: both on
+// sub-partition 3, where two dependent chains interleave without slowing each other down).
+enum { BAR2_FULL = 1, BAR2_DONE = 5, BAR2_EONLY = 9 };  // FULL/DONE: + 2 * stage + parity
+constexpr int kWs2LaunchThreads = kThreads + 64;
+
+template <int G>
+struct Ws2Smem {
+    static constexpr int kXstate = 2 * 2 * 32;                      // float2 [stage][parity][32]
+    static constexpr int kEdge = 2 * kThreads;                      // float2 [stage][kThreads]
+    static constexpr int kTiles = 2 * 2 * G * Geo<G>::ROW;          // float  [stage][parity][G * ROW]
+    static constexpr int bytes = (kXstate + kEdge) * 8 + kTiles * 4;
+};
+
+template <int G, class Core>
+__device__ __forceinline__ void ws2_rec_loop(Core core, float* tiles, float* stp, int lane, int ch, bool ok, int n_tiles, int T,
+                                             int bar_full, int bar_done, int n_ws, bool biquad) {
+    using Q = Geo<G>;
+    float4 s = make_float4(0, 0, 0, 0);
+    if (ok) s = *reinterpret_cast<const float4*>(stp + 4 * (long long)ch);
+    core.load(s);
+    for (int i = 0; i < n_tiles; i++) {
+        const int b = i & 1;
+        const int rem = T - i * Q::S;
+        const int valid_f4 = (rem < Q::S ? rem : Q::S) / 4;
+        bar_sync(bar_full + b, n_ws);
+        if (lane < G) recurrence_row(core, reinterpret_cast<float4*>(tiles + b * (G * Q::ROW) + lane * Q::ROW), valid_f4);
+        __threadfence_block();
+        __syncwarp();
+        bar_arrive(bar_done + b, n_ws);
+    }
+    if (ok) {
+        core.save(s);
+        float* f = stp + 4 * (long long)ch;
+        if (biquad) { f[2] = s.z; f[3] = s.w; }  // y1, y2; the elementwise warps own x1, x2
+        else *reinterpret_cast<float4*>(f) = s;
+    }
+}
+
+template <int G, bool XR>
+__global__ void __launch_bounds__(XR ? kXrLaunchThreads : kWs2LaunchThreads, XR ? 1 : 2)
+fused_kernel_ws2(const __grid_constant__ Program prog, int c_begin, int c_end, long long T64, int r1, int r2) {
+    using Q = Geo<G>;
+    constexpr int n_e = kThreads, n_ws = kThreads + 32;
+    extern __shared__ float4 smem4[];
+    float2* xstate = reinterpret_cast<float2*>(smem4);
+    float2* edge = xstate + Ws2Smem<G>::kXstate;
+    float* tiles = reinterpret_cast<float*>(edge + Ws2Smem<G>::kEdge);
+    const int T = (int)T64;
+    const int nt = (T + Q::S - 1) / Q::S;
+    int t = threadIdx.x, role = 0;  // 0 = elementwise, 1 = R1, 2 = R2
+    if constexpr (XR) {
+        const int pw = t >> 5;
+        if ((pw & 3) == 3) {
+            if (pw > 7) return;
+            role = pw == 3 ? 1 : 2;
+        } else {
+            t = (pw - (pw >> 2)) * 32 + (t & 31);
+            if (t >= n_e) return;
+        }
+    } else if (t >= n_e) {
+        role = 1 + ((t - n_e) >> 5);
+    }
+    const Op& rop1 = prog.ops[r1];
+    const Op& rop2 = prog.ops[r2];
+
+    if (role) {  // ---------------- recurrence warps ----------------
+        const Op& rop = role == 1 ? rop1 : rop2;
+        const int st = role - 1;
+        const int rl = threadIdx.x & 31;
+        const int lane = rl < G ? rl : G;
+        const int ch = c_begin + blockIdx.x * G + lane;
+        const bool ok = lane < G && ch < c_end;
+        float* stp = prog.states[rop.aux];
+        float* tl = tiles + st * (2 * G * Q::ROW);
+        const int bf = BAR2_FULL + 2 * st, bd = BAR2_DONE + 2 * st;
+        if (rop.code == OP_BIQUAD) {
+            DF1Core core; core.a1 = rop.p[3]; core.a2 = rop.a2;
+            ws2_rec_loop<G>(core, tl, stp, lane, ch, ok, nt, T, bf, bd, n_ws, true);
+        } else if (rop.code == OP_LP1) {
+            OnePoleCore core; core.r = rop.p[0];
+            ws2_rec_loop<G>(core, tl, stp, lane, ch, ok, nt, T, bf, bd, n_ws, false);
+        } else {
+            EnvCore core; core.ga = rop.p[0]; core.gr = rop.p[1];
+            ws2_rec_loop<G>(core, tl, stp, lane, ch, ok, nt, T, bf, bd, n_ws, false);
+        }
+        return;
+    }
+
+    // ---------------- elementwise warps ----------------
+    Ctx<G> c;
+    c.prog = &prog;
+    c.t = t;
+    c.g = t / Q::TPC;
+    c.j = t % Q::TPC;
+    c.ch = c_begin + blockIdx.x * G + c.g;
+    c.ch_ok = c.ch < c_end;
+    c.T = T;
+    c.init_streams(prog);
+    c.sm_state = nullptr;
+    c.edge = edge;
+    c.stage = nullptr;
+    c.vregs = nullptr;
+    c.n_tiles = nt;
+    c.tc.tile = tiles;
+    c.tc.g = c.g;
+    c.tc.j = c.j;
+    c.tc.rec_warp = 0;
+    // biquad x1, x2 of each stage, carried from tile to tile: registers (TPC <= 32) or xstate[stage][parity][g]
+    float cx[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+    for (int st = 0; st < 2; st++) {
+        const Op& rop = st == 0 ? rop1 : rop2;
+        if (rop.code != OP_BIQUAD) continue;
+        const float* stp = prog.states[rop.aux];
+        if (Q::TPC <= 32) {
+            if (c.ch_ok) { const float2 s2 = *reinterpret_cast<const float2*>(stp + 4 * (long long)c.ch); cx[st][0] = s2.x; cx[st][1] = s2.y; }
+        } else if (t < G) {
+            const int ch = c_begin + blockIdx.x * G + t;
+            xstate[st * 64 + t] = ch < c_end ? *reinterpret_cast<const float2*>(stp + 4 * (long long)ch) : make_float2(0.f, 0.f);
+        }
+    }
+    Pf pf;
+#pragma unroll
+    for (int i = 0; i < kChunk; i++) pf.in[i] = pf.ring[i] = 0.0f;
+    if (prog.pf_buf[0] >= 0) c.prefetch_in(0, pf.in);
+    if (prog.pf_ring[1] >= 0) c.prefetch_ring(c.ring_slot, c.j * kChunk, pf.ring);
+    bar_sync(BAR2_EONLY, n_e);
+
+    auto set_tile = [&](int ti) {
+        c.tile_i = ti;
+        c.n0 = ti * Q::S + c.j * kChunk;
+        c.active = c.ch_ok && c.n0 < c.T;
+        const int rem = c.T - ti * Q::S;
+        c.tc.valid_f4 = (rem < Q::S ? rem : Q::S) / 4;
+        c.j_last = c.tc.valid_f4 / kF4 - 1;
+    };
+    // prologue + time-parallel part of recurrence op `rop` (stage st) for the tile set by set_tile(ti), then the hand-off
+    auto feed = [&](const Op& rop, int st, int ti, float (&acc)[kChunk]) {
+        if (rop.pre & 1) {
+#pragma unroll
+            for (int k = 0; k < kChunk; k++) acc[k] = add(0.0f, acc[k]);
+        }
+        if (rop.pre & 2) div16(acc, ConstDiv{rop.p[4], rop.p[5]}, rop.pre & 4);
+        if (rop.code == OP_BIQUAD) {
+            const float b0 = rop.p[0], b1 = rop.p[1], b2 = rop.p[2];
+            const float nx1 = acc[kChunk - 1], nx2 = acc[kChunk - 2];
+            float xm1, xm2;
+            if constexpr (Q::TPC <= 32) {
+                xm1 = __shfl_up_sync(0xffffffffu, nx1, 1, Q::TPC);
+                xm2 = __shfl_up_sync(0xffffffffu, nx2, 1, Q::TPC);
+                if (c.j == 0) { xm1 = cx[st][0]; xm2 = cx[st][1]; }
+                cx[st][0] = __shfl_sync(0xffffffffu, nx1, c.j_last, Q::TPC);
+                cx[st][1] = __shfl_sync(0xffffffffu, nx2, c.j_last, Q::TPC);
+            } else {
+                float2* ed = edge + st * kThreads;
+                float2* xs = xstate + st * 64;
+                ed[t] = make_float2(nx2, nx1);
+                bar_sync(BAR2_EONLY, n_e);
+                if (c.j == 0) { const float2 s2 = xs[(ti & 1) * 32 + c.g]; xm1 = s2.x; xm2 = s2.y; }
+                else { const float2 e = ed[t - 1]; xm2 = e.x; xm1 = e.y; }
+                if (c.j == c.j_last) xs[((ti + 1) & 1) * 32 + c.g] = make_float2(nx1, nx2);
+            }
+            float pm1 = acc[0], pm2;
+            acc[0] = add(add(mul(b0, acc[0]), mul(b1, xm1)), mul(b2, xm2));
+            pm2 = pm1; pm1 = acc[1];
+            acc[1] = add(add(mul(b0, acc[1]), mul(b1, pm2)), mul(b2, xm1));
+#pragma unroll
+            for (int k = 2; k < kChunk; k++) {
+                const float xi = acc[k];
+                acc[k] = add(add(mul(b0, xi), mul(b1, pm1)), mul(b2, pm2));
+                pm2 = pm1; pm1 = xi;
+            }
+        } else if (rop.code == OP_LP1) {
+            const float omr = rop.p[1];
+#pragma unroll
+            for (int k = 0; k < kChunk; k++) acc[k] = mul(acc[k], omr);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kChunk; k++) acc[k] = fabsf(acc[k]);
+        }
+        float4* row = reinterpret_cast<float4*>(tiles + (st * 2 + (ti & 1)) * (G * Q::ROW) + c.g * Q::ROW);
+#pragma unroll
+        for (int k = 0; k < kF4; k++)
+            row[kF4 * c.j + (k ^ sw_of(c.j))] = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+        __threadfence_block();
+        bar_arrive(BAR2_FULL + 2 * st + (ti & 1), n_ws);
+    };
+    auto fetch = [&](int st, int ti, float (&acc)[kChunk]) {  // wait for recurrence `st` on tile ti and read it back
+        bar_sync(BAR2_DONE + 2 * st + (ti & 1), n_ws);
+        const float4* row = reinterpret_cast<const float4*>(tiles + (st * 2 + (ti & 1)) * (G * Q::ROW) + c.g * Q::ROW);
+#pragma unroll
+        for (int k = 0; k < kF4; k++) {
+            const float4 q = row[kF4 * c.j + (k ^ sw_of(c.j))];
+            acc[4 * k] = q.x; acc[4 * k + 1] = q.y; acc[4 * k + 2] = q.z; acc[4 * k + 3] = q.w;
+        }
+    };
+
+    // One interpreter call site (the phase loop is not unrolled): phase 0 = ops before recurrence 1 on tile i,
+    // phase 1 = ops between the recurrences on tile i-1, phase 2 = ops after recurrence 2 on tile i-2.
+    const int lo[3] = {0, r1 + 1, r2 + 1}, hi[3] = {r1, r2, prog.n_ops};
+    bar_sync(BAR2_EONLY, n_e);
+    for (int i = 0; i < nt + 2; i++) {
+        // ring stores of a tile's post-ops become visible to the other threads' later ring loads through the DONE
+        // syncs (CTA-scope barriers among all elementwise threads, at least one per iteration from i = 1 on)
+        // (iteration 1 has no DONE sync before its first edge[] write yet: order it behind iteration 0's reads)
+        if (i == 1) bar_sync(BAR2_EONLY, n_e);
+#pragma unroll 1
+        for (int ph = 0; ph < 3; ph++) {
+            const int ti = i - ph;
+            if (ti < 0 || ti >= nt) continue;
+            float acc[kChunk];
+            set_tile(ti);
+            if (ph == 0) {
+#pragma unroll
+                for (int k = 0; k < kChunk; k++) acc[k] = 0.0f;
+            } else {
+                fetch(ph - 1, ti, acc);
+            }
+            for (int ip = lo[ph]; ip < hi[ph]; ip++) exec_op<G>(prog.ops[ip].code, prog.ops[ip].mode, prog.ops[ip].pre, -1, prog.ops[ip], c, acc, pf);
+            if (ph < 2) feed(ph == 0 ? rop1 : rop2, ph, ti, acc);
+        }
+    }
+    bar_sync(BAR2_EONLY, n_e);
+    for (int st = 0; st < 2; st++) {
+        const Op& rop = st == 0 ? rop1 : rop2;
+        if (rop.code != OP_BIQUAD) continue;
+        float* stp = prog.states[rop.aux];
+        if (Q::TPC <= 32) {
+            if (c.j == 0 && c.ch_ok) *reinterpret_cast<float2*>(stp + 4 * (long long)c.ch) = make_float2(cx[st][0], cx[st][1]);
+        } else if (t < G) {
+            const int ch = c_begin + blockIdx.x * G + t;
+            if (ch < c_end) *reinterpret_cast<float2*>(stp + 4 * (long long)ch) = xstate[st * 64 + (nt & 1) * 32 + t];
+        }
+    }
+}
+
+// indices of the two recurrence ops if the program qualifies for fused_kernel_ws2
+bool ws2_rec_indices(const Program& p, int* r1, int* r2) {
+    if (p.n_vregs != 0) return false;
+    int n = 0, idx[2] = {-1, -1};
+    for (int i = 0; i < p.n_ops; i++) {
+        const int c = p.ops[i].code;
+        if (c == OP_BIQUAD || c == OP_LP1 || c == OP_ENVELOPE) {
+            if (n == 2) return false;
+            if (p.ops[i].pflags) return false;
+            idx[n++] = i;
+        }
+        if (c == OP_HP1 || c == OP_SIGGEN) return false;
+    }
+    if (n != 2) return false;
+    *r1 = idx[0];
+    *r2 = idx[1];
+    return true;
+}
+
+template <int G, bool XR>
+int launch_ws2(const Program& prog, int c_begin, int c_end, int64_t T, int r1, int r2, cudaStream_t st) {
+    const int smem = Ws2Smem<G>::bytes;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(fused_kernel_ws2<G, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    const int n_cta = (c_end - c_begin + G - 1) / G;
+    fused_kernel_ws2<G, XR><<<n_cta, XR ? kXrLaunchThreads : kWs2LaunchThreads, smem, st>>>(prog, c_begin, c_end, (long long)T, r1, r2);
+    return (int)cudaGetLastError();
+}
 }  // namespace
 int ws_timing_read(long long* out, bool clear) {
     cudaError_t e = cudaMemcpyFromSymbol(out, g_ws_timing, 8 * sizeof(long long));
@@ -1287,6 +1560,15 @@ template <int G>
 int launch_g(const Program& prog, int c_begin, int c_end, int64_t T, int n_states, cudaStream_t st) {
     static const bool no_static = getenv("DSPB_NO_STATIC") != nullptr;
     static const bool no_ws = getenv("DSPB_NO_WS") != nullptr;
+    {   // two recurrences in series: pipelined over two recurrence warps
+        static const bool no_ws2 = getenv("DSPB_NO_WS2") != nullptr;
+        int r1 = -1, r2 = -1;
+        if (!no_ws && !no_ws2 && G <= 16 && ws2_rec_indices(prog, &r1, &r2) && Ws2Smem<G>::bytes <= 200 * 1024) {
+            // only the chain-bound regime (one CTA per SM, one wave) has a variant: with many channels per SM the
+            // elementwise work dominates and the plain kernel below is as good
+            if ((c_end - c_begin + G - 1) / G <= 128) return launch_ws2<G, true>(prog, c_begin, c_end, T, r1, r2, st);
+        }
+    }
     const int rec = (G <= 32 && !no_ws) ? ws_rec_index(prog) : -1;
     if (rec >= 0 && ws_smem_bytes(prog, G) <= 200 * 1024) {
         // chain-bound launches (at most one CTA per SM and one wave: n_cta <= 8 GPCs x 16 SMs) give the recurrence
