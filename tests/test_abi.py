@@ -90,3 +90,21 @@ def test_planning_mode_describes_every_fir_kernel_and_extension_node(lib):
     g.apply(e)
     plan = e.describe_plan()
     assert "envelope(" in plan and "(extension)" in plan
+
+
+@pytest.mark.parametrize("workload,channels,expect", [
+    ("target", 4096, "G=16"),    # many channels per SM: >= 256 CTAs, the launcher then trims to 8-channel CTAs
+    ("config3", 1024, "G=8"),    # light chain, <= 2048 channels: one wave of <= 128 CTAs (exclusive-R layout)
+    ("config2", 256, "G=2"),
+    ("config5", 1024, "G=4"),    # heavy graph segment (17 ops, shared-memory vregs): 256 CTAs at two per SM
+])
+def test_tile_geometry_heuristic(lib, workload, channels, expect):
+    """The scheduler's CTA geometry (csrc/engine.cpp close_fused) for the BASELINE configs, without a GPU."""
+    from dsp_stuff_b200 import signals as S
+    from dsp_stuff_b200.engine import Engine
+
+    e = Engine(channels, block=1024, max_samples=16384, device=-1)
+    S.WORKLOADS[workload][0]().apply(e)
+    plan = e.describe_plan()
+    segs = [l for l in plan.splitlines() if "fused segment" in l]
+    assert any(expect + " " in l for l in segs), segs
