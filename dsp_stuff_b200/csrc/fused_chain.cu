@@ -6,10 +6,12 @@
 //
 // Geometry: a CTA owns G channels for the whole call and walks time in tiles of S = 4096/G samples,
 // so every sequential dependency (IIR state, comb ring, Fuzz 128-sample blocks) stays inside one
-// CTA.  256 threads; thread (g, j) holds 16 consecutive samples of channel g in registers (`acc`).
-// HBM traffic is 128-bit per thread (4 x 16 B per 16 samples); the next tile's input and ring reads
-// are prefetched with cp.async into thread-private shared-memory staging right after the current
-// tile has consumed them, so they are in flight while the tile computes.
+// CTA.  512 elementwise threads; thread (g, j) holds 8 consecutive samples of channel g in registers (`acc`).
+// HBM traffic is 128-bit per thread; the next tile's input and ring chunks are prefetched one tile ahead
+// straight into registers.  Three kernels share the op code below:
+//   fused_kernel      any program (run-time interpreter or a compile-time chain), recurrences in place
+//   fused_kernel_ws   one recurrence: warp-specialised pipeline (elementwise warps + one recurrence warp)
+//   fused_kernel_ws2  two recurrences in series: two recurrence warps, three-phase pipeline
 //
 // Recurrences (biquad / one-pole / envelope) are bit-identical to the reference: everything that
 // does not depend on the previous OUTPUT (the feed-forward taps) is computed time-parallel with the
@@ -84,15 +86,6 @@ __device__ __forceinline__ float block128_max_abs(const float (&v)[kChunk]) {
     for (int d = 1; d < kBlk; d <<= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
     return __uint_as_float(m);
 }
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_but_three() { asm volatile("cp.async.wait_group 3;\n" ::: "memory"); }
 
 __device__ __forceinline__ float4 ldg_stream(const float4* p) {
     float4 r;
@@ -727,7 +720,7 @@ struct ChainGDBR {  // src -> gain -> distort(SoftClip) -> biquad -> reverb -> s
 template <int PF>
 struct ChainGDR {  // src -> gain -> distort(SoftClip) -> reverb -> store   (config 1)
     static constexpr int n = 5;
-    static constexpr int rec = -1;
+    [[maybe_unused]] static constexpr int rec = -1;
     __host__ __device__ static constexpr int pf_of(int i) { return i == 0 ? (PF & 1) : i == 3 ? ((PF >> 1) & 1) : i == n - 1 ? 1 : 0; }
     __host__ __device__ static constexpr int sig(int i) {
         return i == 0 ? DSPB_SIG(OP_LOADG, 0, 0) : i == 1 ? DSPB_SIG(OP_GAIN, 0, 6) : i == 2 ? DSPB_SIG(OP_DISTORT, SoftClip, 7)
@@ -737,7 +730,7 @@ struct ChainGDR {  // src -> gain -> distort(SoftClip) -> reverb -> store   (con
 template <int PF>
 struct ChainBB {  // src -> biquad -> biquad -> store   (config 2)
     static constexpr int n = 4;
-    static constexpr int rec = -1;
+    [[maybe_unused]] static constexpr int rec = -1;
     __host__ __device__ static constexpr int pf_of(int i) { return i == 0 ? (PF & 1) : i == -1 ? ((PF >> 1) & 1) : i == n - 1 ? 1 : 0; }
     __host__ __device__ static constexpr int sig(int i) {
         return i == 0 ? DSPB_SIG(OP_LOADG, 0, 0) : i == 1 ? DSPB_SIG(OP_BIQUAD, 0, 6) : i == 2 ? DSPB_SIG(OP_BIQUAD, 0, 7) : DSPB_SIG(OP_STOREG, 0, 7);
@@ -746,7 +739,7 @@ struct ChainBB {  // src -> biquad -> biquad -> store   (config 2)
 template <int PF>
 struct ChainLH {  // src -> low_pass -> high_pass -> store   (config 2, one-pole variant)
     static constexpr int n = 4;
-    static constexpr int rec = -1;
+    [[maybe_unused]] static constexpr int rec = -1;
     __host__ __device__ static constexpr int pf_of(int i) { return i == 0 ? (PF & 1) : i == -1 ? ((PF >> 1) & 1) : i == n - 1 ? 1 : 0; }
     __host__ __device__ static constexpr int sig(int i) {
         return i == 0 ? DSPB_SIG(OP_LOADG, 0, 0) : i == 1 ? DSPB_SIG(OP_LP1, 0, 6) : i == 2 ? DSPB_SIG(OP_HP1, 0, 7) : DSPB_SIG(OP_STOREG, 0, 7);
@@ -755,7 +748,7 @@ struct ChainLH {  // src -> low_pass -> high_pass -> store   (config 2, one-pole
 template <int PF>
 struct ChainCopy {  // G -> (/nf) -> store   (the segment after a Fir node)
     static constexpr int n = 2;
-    static constexpr int rec = -1;
+    [[maybe_unused]] static constexpr int rec = -1;
     __host__ __device__ static constexpr int pf_of(int i) { return i == 0 ? (PF & 1) : i == -1 ? ((PF >> 1) & 1) : i == n - 1 ? 1 : 0; }
     __host__ __device__ static constexpr int sig(int i) { return i == 0 ? DSPB_SIG(OP_LOADG, 0, 0) : DSPB_SIG(OP_STOREG, 0, 6); }
 };
@@ -1042,7 +1035,6 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
 #ifdef DSPB_WS_TIMING
         if (blockIdx.x == 0 && t == 0) g_ws_timing[5] += clock64() - tb0;
 #endif
-        cp_async_wait_all();
         float acc[kChunk];
 #ifdef DSPB_WS_TIMING
         long long te0 = clock64(), te1 = te0, te2 = te0;
