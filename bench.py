@@ -56,7 +56,7 @@ TRAFFIC = {
     ("target", "fused", 4096, 16384): 539587328 + 487191552,   # profiles/r01s4_target_fused_chain_kernel.txt
 }
 
-DEFAULT_CHANNELS = {"config1": 2, "config2": 256, "config3": 1024, "config4": 4096, "config5": 1024, "target": 4096}
+DEFAULT_CHANNELS = {"config1": 2, "config2": 256, "config2_one_pole": 256, "config3": 1024, "config4": 4096, "config5": 1024, "target": 4096}
 
 
 def load_peaks():

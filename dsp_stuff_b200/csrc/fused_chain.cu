@@ -925,10 +925,13 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
     float2* xstate = reinterpret_cast<float2*>(smem4);
     float2* edge = xstate + 64;  // xstate[2][32]: read parity i & 1, written parity (i + 1) & 1
     float* tiles = reinterpret_cast<float*>(edge + kThreads);
-    float4* stage = reinterpret_cast<float4*>(tiles + 2 * G * Q::ROW);
     const long long n_tiles = (T + Q::S - 1) / Q::S;
     const Op& rop = prog.ops[rec_index];
     const int rcode = Chain::n > 0 ? (Chain::sig(Chain::rec) & 0xff) : rop.code;
+    // high_pass (y = x - z, nodes/high_pass.rs:36-41) needs x again after the recurrence: kept in a second pair of
+    // tile buffers, same thread-private positions
+    float* keep = tiles + 2 * G * Q::ROW;
+    float4* stage = reinterpret_cast<float4*>(keep + (rcode == OP_HP1 ? 2 * G * Q::ROW : 0));
     float* stp = prog.states[rop.aux];
 
     if (t >= n_e) {  // ---------------- R warps ----------------
@@ -969,7 +972,7 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
                 bar_arrive(BAR_DONE0 + b, n_ws);
             }
             if (ok) { float* f = reinterpret_cast<float*>(sout); f[2] = core.y1; f[3] = core.y2; }
-        } else if (rcode == OP_LP1) {
+        } else if (rcode == OP_LP1 || rcode == OP_HP1) {
             OnePoleCore core; core.r = rop.p[0];
             ws_recurrence_warp<G>(core, tiles, sin, sout, lane, ok, n_tiles, T, n_ws);
         } else {
@@ -1091,7 +1094,13 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
                 if constexpr (Q::TPC > 32) {
                     if (c.j == c.j_last) xstate[((i + 1) & 1) * 32 + c.g] = make_float2(nx1, nx2);
                 }
-            } else if (rcode == OP_LP1) {
+            } else if (rcode == OP_LP1 || rcode == OP_HP1) {
+                if (rcode == OP_HP1) {
+                    float4* krow = reinterpret_cast<float4*>(keep + (int)(i & 1) * (G * Q::ROW) + c.g * Q::ROW);
+#pragma unroll
+                    for (int k = 0; k < kF4; k++)
+                        krow[kF4 * c.j + (k ^ sw_of(c.j))] = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+                }
                 const float omr = rop.p[1];
 #pragma unroll
                 for (int k = 0; k < kChunk; k++) acc[k] = mul(acc[k], omr);
@@ -1121,6 +1130,15 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
             for (int k = 0; k < kF4; k++) {
                 const float4 q = row[kF4 * c.j + (k ^ sw_of(c.j))];
                 acc[4 * k] = q.x; acc[4 * k + 1] = q.y; acc[4 * k + 2] = q.z; acc[4 * k + 3] = q.w;
+            }
+            if (rcode == OP_HP1) {  // y = x - z
+                const float4* krow = reinterpret_cast<const float4*>(keep + b * (G * Q::ROW) + c.g * Q::ROW);
+#pragma unroll
+                for (int k = 0; k < kF4; k++) {
+                    const float4 x = krow[kF4 * c.j + (k ^ sw_of(c.j))];
+                    acc[4 * k] = sub(x.x, acc[4 * k]); acc[4 * k + 1] = sub(x.y, acc[4 * k + 1]);
+                    acc[4 * k + 2] = sub(x.z, acc[4 * k + 2]); acc[4 * k + 3] = sub(x.w, acc[4 * k + 3]);
+                }
             }
             if constexpr (Chain::n > 0) run_static_range<G, Chain, Chain::rec + 1, Chain::n>(prog, c, acc, pf);
             else
@@ -1156,7 +1174,7 @@ struct Ws2Smem {
     static constexpr int kXstate = 2 * 2 * 32;                      // float2 [stage][parity][32]
     static constexpr int kEdge = 2 * kThreads;                      // float2 [stage][kThreads]
     static constexpr int kTiles = 2 * 2 * G * Geo<G>::ROW;          // float  [stage][parity][G * ROW]
-    static constexpr int bytes = (kXstate + kEdge) * 8 + kTiles * 4;
+    static constexpr int bytes = (kXstate + kEdge) * 8 + 2 * kTiles * 4;  // tiles + the high_pass keep buffers
 };
 
 template <int G, class Core>
@@ -1193,6 +1211,7 @@ fused_kernel_ws2(const __grid_constant__ Program prog, int c_begin, int c_end, l
     float2* xstate = reinterpret_cast<float2*>(smem4);
     float2* edge = xstate + Ws2Smem<G>::kXstate;
     float* tiles = reinterpret_cast<float*>(edge + Ws2Smem<G>::kEdge);
+    float* keep = tiles + Ws2Smem<G>::kTiles;  // x of a high_pass stage, [stage][parity][G * ROW]
     const int T = (int)T64;
     const int nt = (T + Q::S - 1) / Q::S;
     int t = threadIdx.x, role = 0;  // 0 = elementwise, 1 = R1, 2 = R2
@@ -1224,7 +1243,7 @@ fused_kernel_ws2(const __grid_constant__ Program prog, int c_begin, int c_end, l
         if (rop.code == OP_BIQUAD) {
             DF1Core core; core.a1 = rop.p[3]; core.a2 = rop.a2;
             ws2_rec_loop<G>(core, tl, stp, lane, ch, ok, nt, T, bf, bd, n_ws, true);
-        } else if (rop.code == OP_LP1) {
+        } else if (rop.code == OP_LP1 || rop.code == OP_HP1) {
             OnePoleCore core; core.r = rop.p[0];
             ws2_rec_loop<G>(core, tl, stp, lane, ch, ok, nt, T, bf, bd, n_ws, false);
         } else {
@@ -1317,7 +1336,13 @@ fused_kernel_ws2(const __grid_constant__ Program prog, int c_begin, int c_end, l
                 acc[k] = add(add(mul(b0, xi), mul(b1, pm1)), mul(b2, pm2));
                 pm2 = pm1; pm1 = xi;
             }
-        } else if (rop.code == OP_LP1) {
+        } else if (rop.code == OP_LP1 || rop.code == OP_HP1) {
+            if (rop.code == OP_HP1) {
+                float4* krow = reinterpret_cast<float4*>(keep + (st * 2 + (ti & 1)) * (G * Q::ROW) + c.g * Q::ROW);
+#pragma unroll
+                for (int k = 0; k < kF4; k++)
+                    krow[kF4 * c.j + (k ^ sw_of(c.j))] = make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]);
+            }
             const float omr = rop.p[1];
 #pragma unroll
             for (int k = 0; k < kChunk; k++) acc[k] = mul(acc[k], omr);
@@ -1339,6 +1364,15 @@ fused_kernel_ws2(const __grid_constant__ Program prog, int c_begin, int c_end, l
         for (int k = 0; k < kF4; k++) {
             const float4 q = row[kF4 * c.j + (k ^ sw_of(c.j))];
             acc[4 * k] = q.x; acc[4 * k + 1] = q.y; acc[4 * k + 2] = q.z; acc[4 * k + 3] = q.w;
+        }
+        if ((st == 0 ? rop1 : rop2).code == OP_HP1) {  // y = x - z (nodes/high_pass.rs:36-41)
+            const float4* krow = reinterpret_cast<const float4*>(keep + (st * 2 + (ti & 1)) * (G * Q::ROW) + c.g * Q::ROW);
+#pragma unroll
+            for (int k = 0; k < kF4; k++) {
+                const float4 x = krow[kF4 * c.j + (k ^ sw_of(c.j))];
+                acc[4 * k] = sub(x.x, acc[4 * k]); acc[4 * k + 1] = sub(x.y, acc[4 * k + 1]);
+                acc[4 * k + 2] = sub(x.z, acc[4 * k + 2]); acc[4 * k + 3] = sub(x.w, acc[4 * k + 3]);
+            }
         }
     };
 
@@ -1387,12 +1421,12 @@ bool ws2_rec_indices(const Program& p, int* r1, int* r2) {
     int n = 0, idx[2] = {-1, -1};
     for (int i = 0; i < p.n_ops; i++) {
         const int c = p.ops[i].code;
-        if (c == OP_BIQUAD || c == OP_LP1 || c == OP_ENVELOPE) {
+        if (c == OP_BIQUAD || c == OP_LP1 || c == OP_HP1 || c == OP_ENVELOPE) {
             if (n == 2) return false;
             if (p.ops[i].pflags) return false;
             idx[n++] = i;
         }
-        if (c == OP_HP1 || c == OP_SIGGEN) return false;
+        if (c == OP_SIGGEN) return false;
     }
     if (n != 2) return false;
     *r1 = idx[0];
@@ -1425,7 +1459,9 @@ int ws_timing_read(long long* out, bool clear) {
 namespace {
 int ws_smem_bytes(const Program& prog, int G) {
     const int S = kTile / G;
-    return 64 * 8 + kThreads * 8 + 2 * G * (S + 4) * 4 + prog.n_vregs * kTile * 4;
+    bool hp = false;
+    for (int i = 0; i < prog.n_ops; i++) hp = hp || prog.ops[i].code == OP_HP1;
+    return 64 * 8 + kThreads * 8 + (hp ? 4 : 2) * G * (S + 4) * 4 + prog.n_vregs * kTile * 4;
 }
 // does op read / write shared-memory vreg v?
 bool op_reads_vreg(const Op& op, int v) {
@@ -1443,11 +1479,11 @@ int ws_rec_index(const Program& p) {
     int idx = -1;
     for (int i = 0; i < p.n_ops; i++) {
         const int c = p.ops[i].code;
-        if (c == OP_BIQUAD || c == OP_LP1 || c == OP_ENVELOPE) {
+        if (c == OP_BIQUAD || c == OP_LP1 || c == OP_HP1 || c == OP_ENVELOPE) {
             if (idx >= 0) return -1;
             idx = i;
         }
-        if (c == OP_HP1 || c == OP_SIGGEN) return -1;
+        if (c == OP_SIGGEN) return -1;
     }
     if (idx < 0) return -1;
     for (int v = 0; v < p.n_vregs; v++) {

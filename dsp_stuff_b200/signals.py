@@ -139,6 +139,7 @@ def config5(n_taps: int = 4096) -> GraphSpec:
 WORKLOADS = {
     "config1": (config1, 16),
     "config2": (config2, 8),
+    "config2_one_pole": (lambda: config2(one_pole=True), 8),   # LowPass(0.9) -> HighPass(0.99), SURVEY §8d config 2 variant
     "config3": (config3, 16),
     "config4": (config4, 8),
     "config5": (config5, 24),
