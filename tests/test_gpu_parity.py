@@ -335,3 +335,60 @@ def test_node_process_matches_simple_node_contract(oracle_mod):
     assert_bit_exact(e2.node_process(4, [x])[0], o.node_process(4, [x])[0], "fir (direct)")
     o.reset_state()   # the oracle's fir already consumed one call above; compare the FFT path from a fresh state
     assert_audio_close(e.node_process(4, [x])[0], o.node_process(4, [x])[0], what="fir (fft)")
+
+
+# ---- launch shapes at BASELINE widths -----------------------------------------------------------------------------
+# The fused kernels pick their CTA geometry from the channel count of the launch (8-channel CTAs in one wave, the
+# exclusive-R layout for <= 128 CTAs, two pipelined recurrence warps, shared-memory vregs next to the pipeline, the
+# plain kernel above those limits).  Small-channel tests never reach most of these shapes, so each is run here at a
+# width that selects it, device-resident (one launch over all channels), and a channel subset is checked against the
+# oracle -- channels are independent.
+def _full_width(oracle_mod, spec, C, n, exact=True, fir_mode=FIR_DIRECT, calls=2):
+    import torch
+
+    x = S.noise(C, n * calls)
+    e = make_engine(spec, C, n, fir_mode=fir_mode)
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.empty_like(xd)
+    for k in range(calls):  # state carried across calls
+        xin = xd[:, k * n:(k + 1) * n].contiguous()
+        yout = torch.empty_like(xin)
+        e.process_device([xin], [yout], n)
+        yd[:, k * n:(k + 1) * n] = yout
+    torch.cuda.synchronize()
+    y = yd.cpu().numpy()
+    sel = sorted({0, 1, 7, 8, 13, 14, 15, 16, 255 % C, C // 2 + 3, C - 2, C - 1})
+    o = make_oracle(oracle_mod, spec, len(sel))
+    ref = np.concatenate([o.process(x[sel][:, k * n:(k + 1) * n])[0] for k in range(calls)], axis=1)
+    if exact:
+        assert_bit_exact(y[sel], ref, f"C={C}")
+    else:
+        assert_audio_close(y[sel], ref, what=f"C={C}")
+    return e
+
+
+@pytest.mark.parametrize("name,C,n", [
+    ("config3", 4096, 128 * 24),           # one recurrence, 8-channel CTAs (512 CTAs, four per SM)
+    ("config3", 2048, 128 * 24),           # exclusive-R layout, G = 16
+    ("config2", 256, 128 * 40),            # two pipelined recurrence warps, G = 2 (BASELINE config 2 width)
+    ("config2", 1024, 128 * 24),           # same, G = 8
+    ("config2", 4096, 128 * 16),           # above 128 CTAs: the plain kernel, static biquad-biquad chain
+    ("config2_one_pole", 256, 128 * 40),   # low_pass -> high_pass on two recurrence warps (x kept for y = x - z)
+    ("config2_one_pole", 4096, 128 * 16),
+    ("config1", 4096, 128 * 24),           # no recurrence
+])
+def test_full_width_launch_shapes_bit_exact(oracle_mod, name, C, n):
+    spec = S.WORKLOADS[name][0]()
+    _full_width(oracle_mod, spec, C, n, exact=True)
+
+
+def test_full_width_config5_graph(oracle_mod):
+    """BASELINE config 5 per-GPU width (1024 channels): the 17-op segment with shared-memory vregs runs in the
+    warp-specialised kernel (G = 4); Tanh on path A -> tolerance."""
+    e = _full_width(oracle_mod, S.config5(n_taps=256), 1024, 128 * 24, exact=False)
+    assert "G=4" in e.describe_plan()
+
+
+def test_full_width_target_chain(oracle_mod):
+    """north_star target width (4096 channels), short taps through the exact FIR path: bit-exact end to end."""
+    _full_width(oracle_mod, S.target_chain(n_taps=128), 4096, 128 * 16, exact=True)
