@@ -887,7 +887,7 @@ int ensure_resources(dspb_engine* e) {
             if (toep) {
                 r = n.toep_tiles.alloc(fir_toeplitz_tiles_bytes(N), false);
                 if (r) return r;
-                r = n.toep_split.alloc(fir_toeplitz_split_bytes(N, C, maxn), false);
+                r = n.toep_split.alloc(fir_toeplitz_split_bytes(N, C, maxn), true);  // rows beyond C stay zero
                 if (r) return r;
             }
             if (!e->plan_only) {
