@@ -108,3 +108,53 @@ def test_tile_geometry_heuristic(lib, workload, channels, expect):
     plan = e.describe_plan()
     segs = [l for l in plan.splitlines() if "fused segment" in l]
     assert any(expect + " " in l for l in segs), segs
+
+
+def test_engine_registry_mirrors_the_dsp_attributes(lib):
+    """Product-side node registry (csrc/engine.cpp kNodeTypes) against SURVEY.md Appendix A: port names in index order
+    (declared input= attrs, then slider(as_input) fields in struct order, lib.rs:191-219), through the C ABI in
+    planning mode (no GPU)."""
+    from dsp_stuff_b200 import NODE_PORTS
+    from dsp_stuff_b200.engine import Engine, EngineError
+
+    appendix_a = {
+        "gain": (("in", "level"), ("out",)), "distort": (("in", "level"), ("out",)),
+        "overdrive": (("in", "boost", "drive", "level"), ("out",)), "chebyshev": (("in",), ("out",)),
+        "biquad": (("in",), ("out",)), "low_pass": (("in",), ("out",)), "high_pass": (("in",), ("out",)),
+        "reverb": (("in",), ("out",)), "fir": (("in",), ("out",)), "add": (("a", "b"), ("out",)),
+        "mix": (("a", "b", "ratio"), ("out",)), "mux": (("a", "b"), ("out",)), "demux": (("in",), ("a", "b")),
+        "envelope": (("in",), ("out",)), "signal_gen": (("amplitude", "frequency"), ("out",)),
+        "input": ((), ("out",)), "output": (("in",), ()),
+    }
+    e = Engine(4, device=-1)
+    for i, (typename, (ins, outs)) in enumerate(appendix_a.items()):
+        e.add_node(typename, 100 + i)
+        assert NODE_PORTS[typename] == (ins, outs), typename          # the Python mirror
+        assert e.get_i64(100 + i, "n_inputs") == len(ins) and e.get_i64(100 + i, "n_outputs") == len(outs), typename
+        assert [e.port_index(100 + i, p) for p in ins] == list(range(len(ins))), typename
+        assert [e.port_index(100 + i, p, True) for p in outs] == list(range(len(outs))), typename
+        with pytest.raises(EngineError):
+            e.port_index(100 + i, "no_such_port")
+    with pytest.raises(EngineError):
+        e.add_node("muff", 999)        # GPL dependency, out of scope: unknown typename is an error code, not a panic
+    with pytest.raises(EngineError):
+        e.add_node("gain", 100)        # duplicate id
+
+
+def test_engine_rejects_cycles_and_unknown_ports_with_status_codes(lib):
+    from dsp_stuff_b200.engine import Engine, EngineError
+
+    e = Engine(2, device=-1)
+    for i, t in enumerate(["input", "gain", "gain", "output"]):
+        e.add_node(t, i)
+    e.link(0, "out", 1, "in")
+    e.link(1, "out", 2, "in")
+    e.link(2, "out", 1, "in")          # cycle: a deadlock in the reference (runtime.rs:568), DSPB_ERR_GRAPH here
+    e.link(2, "out", 3, "in")
+    with pytest.raises(EngineError) as ei:
+        e.compile()
+    assert "cycl" in str(ei.value).lower()
+    with pytest.raises(EngineError):
+        e.link(0, "nope", 1, "in")
+    with pytest.raises(EngineError):
+        e.set_f32(1, "no_such_field", 1.0)
