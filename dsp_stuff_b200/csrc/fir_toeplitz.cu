@@ -9,6 +9,10 @@
 // products of f32 samples and f64 taps; bf16 tensor-core inputs reach the 1e-5 parity bar by splitting
 // both operands into hi + lo bf16 parts (16 mantissa bits) and issuing three MMAs per K step
 // (hi*hi + hi*lo + lo*hi, fp32 accumulation in TMEM): measured ~5e-6 peak-relative on the config-4 input.
+// Error budget: hi + lo represents an operand to 2^-18 relative (two 8-bit significands + the rounding of lo), the
+// dropped lo*lo term is another 2^-18, so each product carries <= ~2^-16.4 relative error with random sign; summed
+// over the taps that is ~2^-17 of ||h||_2 * rms(x), i.e. a few 1e-6 of the output peak (a numpy model of the split
+// gives 4.6e-6, the device 4.2e-6 .. 6.9e-6).  A third split term (6 MMAs) would reach 1e-8 at twice the cost.
 //
 // Operand staging without tensor maps: both operands are written ONCE by small pre-pass kernels into
 // global memory already in the shared-memory image the UMMA descriptors expect (K-major, no swizzle:
