@@ -158,3 +158,30 @@ def test_engine_rejects_cycles_and_unknown_ports_with_status_codes(lib):
         e.link(0, "nope", 1, "in")
     with pytest.raises(EngineError):
         e.set_f32(1, "no_such_field", 1.0)
+
+
+@pytest.mark.parametrize("name,expect", [
+    ("config1", ["gain#", "distort[SoftClip]", "ring*0.5"]),
+    ("config2", ["DF1(", "biquad#"]),
+    ("config3", ["gain#", "distort[SoftClip]", "DF1(", "D=12288"]),
+    ("config5_64taps", ["fir step", "mix#", "add#", "D=6144", "acc /= 2.00010014"]),
+    ("target_256taps", ["fir step", "256 taps", "D=12288"]),
+])
+def test_saved_graph_json_lowers_in_planning_mode(lib, name, expect):
+    """The C++ saved-graph loader (dspb_load_graph_json, reference DSPConfig format: runtime.rs:44-48, 606-612) and
+    the scheduler on the committed fixture graphs, without a GPU."""
+    from dsp_stuff_b200.engine import Engine, EngineError
+
+    text = open(os.path.join(ROOT, "tests", "golden", f"{name}_graph.json")).read()
+    e = Engine(64, block=128, max_samples=128 * 8, device=-1)
+    e.load_graph_json(text)
+    plan = e.describe_plan()
+    for s in expect:
+        assert s in plan, (s, plan)
+    with pytest.raises(EngineError):          # planning mode never processes: no CPU fallback
+        import numpy as np
+        e.process(np.zeros((64, 128), np.float32))
+    with pytest.raises(EngineError):
+        Engine(4, device=-1).load_graph_json('{"nodes": [{"id": 0, "typename": "no_such_node", "position": [0, 0], "cfg": {}}], "links": []}')
+    with pytest.raises(EngineError):
+        Engine(4, device=-1).load_graph_json('{"nodes": [')
