@@ -154,8 +154,13 @@ def cpu_baseline(spec, budget_s):
     rate, dt = time_oracle(spec, cores, n0, cores)
     n = int(max(1024, min(48000 * 120, rate * budget_s / cores)) // 128 * 128)
     rate, dt = time_oracle(spec, cores, n, cores)
+    # SURVEY §8d also asks for the single-thread figure: one channel, ~2 s
+    r1, _ = time_oracle(spec, 1, n0, 1)
+    n1 = int(max(1024, min(48000 * 60, r1 * 2.0)) // 128 * 128)
+    r1, dt1 = time_oracle(spec, 1, n1, 1)
     return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{cores} channels x {n} samples of the same graph and noise input, {cores} threads (one channel each), {dt:.1f} s"}
+            "sample": f"{cores} channels x {n} samples of the same graph and noise input, {cores} threads (one channel each), {dt:.1f} s",
+            "single_thread": {"value": r1, "unit": UNIT, "cores": 1, "sample": f"1 channel x {n1} samples, {dt1:.1f} s"}}
 
 
 def run_reference(args, spec, alg_bytes, C, n):
