@@ -18,6 +18,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <string>
 #include <vector>
@@ -104,19 +105,19 @@ const NodeType kNodeTypes[T_COUNT] = {
     /* output     nodes/output.rs:12-22   */ {"output", {"in"}, {}, {}, {}},
 };
 
-bool g_plan_only = false;  // device == -1: build and describe schedules only; nothing can run
-
+// Planning-only engines (device == -1: build and describe schedules, nothing can run) are a PER-ENGINE property:
+// a planning engine and a real engine may live in one process, on different threads.
 struct DevBuf {  // owning device allocation
     float* p = nullptr;
     size_t bytes = 0;
     bool fake = false;
     ~DevBuf() { if (p && !fake) cudaFree(p); }
-    int alloc(size_t n_bytes, bool zero) {
+    int alloc(size_t n_bytes, bool zero, bool plan_only) {
         if (p && !fake) cudaFree(p);
         p = nullptr;
         bytes = 0;
         if (n_bytes == 0) return DSPB_OK;
-        if (g_plan_only) { fake = true; p = reinterpret_cast<float*>(uintptr_t(16)); bytes = n_bytes; return DSPB_OK; }
+        if (plan_only) { fake = true; p = reinterpret_cast<float*>(uintptr_t(16)); bytes = n_bytes; return DSPB_OK; }
         cudaError_t e = cudaMalloc(&p, n_bytes);
         if (e != cudaSuccess) { p = nullptr; return fail(DSPB_ERR_NOMEM, "cudaMalloc(%zu): %s", n_bytes, cudaGetErrorString(e)); }
         bytes = n_bytes;
@@ -234,25 +235,26 @@ int64_t round_up(int64_t n, int64_t g) { return g <= 1 ? n : (n + g - 1) / g * g
 // (measured: 0.3, 29.99, ... have millions of wrong quotients), so a divisor gets the fast path only
 // after the device has enumerated all 2^32 dividends against IEEE division with zero mismatches
 // (verify_const_div, a few ms, cached per process).  Everything else takes __fdiv_rn.
-bool div_const_ok(float b) {
+bool div_const_ok(float b, bool plan_only) {
     if (!(b > 0.0f) || !std::isfinite(b) || b < 1e-30f || b > 1e30f) return false;
+    if (plan_only) return true;  // nothing runs in planning-only mode; show the optimistic schedule
+    // the verdict is IEEE arithmetic, identical on every device: one process-wide cache, serialised (engines on
+    // different threads compile concurrently; the enumeration itself runs on the calling engine's device)
+    static std::mutex mu;
     static std::map<uint32_t, bool> cache;
     uint32_t bits;
     memcpy(&bits, &b, 4);
+    std::lock_guard<std::mutex> lk(mu);
     auto it = cache.find(bits);
     if (it != cache.end()) return it->second;
     bool ok = false;
-    if (g_plan_only) {
-        ok = true;  // nothing runs in planning-only mode; show the optimistic schedule
-    } else {
-        unsigned long long mism = 1;
-        if (verify_const_div(b, 1.0f / b, &mism) == 0) ok = mism == 0;
-        cache[bits] = ok;
-    }
+    unsigned long long mism = 1;
+    if (verify_const_div(b, 1.0f / b, &mism) == 0) ok = mism == 0;
+    cache[bits] = ok;
     return ok;
 }
-void set_const_div(Op& op, int p_b, int p_r, float b) {
-    const bool ok = div_const_ok(b);
+void set_const_div(Op& op, int p_b, int p_r, float b, bool plan_only) {
+    const bool ok = div_const_ok(b, plan_only);
     op.p[p_b] = b;
     op.p[p_r] = ok ? 1.0f / b : 0.0f;
     op.pad = ok ? 1 : 0;
@@ -345,8 +347,14 @@ struct Lowerer {
             return;
         }
         if (v.where == Value::ZERO || v.where == Value::NONE) {
-            if (first) emit(mk(OP_ZERO), "acc = 0                      ; " + what);
-            return;  // adding +0.0 changes nothing but the sign of a zero
+            if (first) {
+                emit(mk(OP_ZERO), "acc = 0                      ; " + what);
+            } else {  // acc + 0.0 only turns a -0.0 sum into +0.0; kept so that the sign of a zero matches node.rs:181-183
+                Op z = mk(OP_LOADV);
+                z.vreg = 0xFF;
+                emit(z, "acc = 0.0 + acc              ; " + what + " (all-zero link)");
+            }
+            return;
         }
         if (v.where == Value::VREG) {
             Op o = mk(first ? OP_LOADV : OP_ADDV);
@@ -376,7 +384,7 @@ struct Lowerer {
         }
         if (e.raw_ports) return true;  // dspb_node_process: inputs are already averaged (node.rs:217-222)
         Op d = mk(OP_DIVC);
-        set_const_div(d, 0, 1, nf);
+        set_const_div(d, 0, 1, nf, e.plan_only);
         char b[96];
         snprintf(b, sizeof b, "acc /= %.9g           ; fan-in average of %zu link(s)", nf, ls.size());
         emit(d, b);
@@ -416,10 +424,14 @@ struct Lowerer {
     int finish_vregs(Step& st, std::vector<Op>& o, std::vector<std::string>& t);
 };
 
+// Ops whose `vreg` field names a shared-memory vreg they READ (one predicate for liveness, remapping and the kernels'
+// op_reads_vreg: a code missing from one of those lists reads a slot that was never allocated).
+bool reads_vreg_operand(int code) { return op_reads_vreg_field(code); }
+
 // Peephole + vreg allocation for one fused step.  Virtual vregs -> shared-memory slots by liveness.
 int Lowerer::finish_vregs(Step& st, std::vector<Op>& o, std::vector<std::string>& t) {
     auto reads = [](const Op& op, int v) {
-        if ((op.code == OP_LOADV || op.code == OP_ADDV || op.code == OP_COPYV || op.code == OP_ADD || op.code == OP_MIX || op.code == OP_GATE) && op.vreg == v) return true;
+        if (reads_vreg_operand(op.code) && op.vreg == v) return true;
         for (int i = 0; i < 3; i++)
             if ((op.pflags & (1 << i)) && op.pv[i] == v) return true;
         return false;
@@ -496,7 +508,7 @@ int Lowerer::finish_vregs(Step& st, std::vector<Op>& o, std::vector<std::string>
         phys[v] = s;
     }
     for (auto& op : o) {
-        if ((op.code == OP_LOADV || op.code == OP_ADDV || op.code == OP_COPYV || op.code == OP_ADD || op.code == OP_MIX || op.code == OP_SAVEV) && op.vreg != 0xFF)
+        if ((reads_vreg_operand(op.code) || op.code == OP_SAVEV) && op.vreg != 0xFF)
             op.vreg = (uint8_t)phys[op.vreg];
         for (int i = 0; i < 3; i++)
             if (op.pflags & (1 << i)) op.pv[i] = (uint8_t)phys[op.pv[i]];
@@ -551,6 +563,11 @@ void Lowerer::close_fused() {
     static const bool in_prefetch = !(getenv("DSPB_IN_PREFETCH") && atoi(getenv("DSPB_IN_PREFETCH")) == 0);
     for (int i = 0; i < P.n_ops && in_prefetch; i++)
         if (P.ops[i].code == OP_LOADG) {
+            // A buffer this very program stores earlier (a source value spilled for a later step AND consumed again in
+            // this one) must not be read one tile ahead: the prefetch would see the previous call's scratch.
+            bool stored_here = false;
+            for (int k = 0; k < i; k++) stored_here = stored_here || (P.ops[k].code == OP_STOREG && P.ops[k].buf == P.ops[i].buf);
+            if (stored_here) continue;
             P.pf_buf[0] = P.ops[i].buf;
             P.ops[i].aux = 1;
             P.n_prefetch++;
@@ -585,6 +602,20 @@ void Lowerer::close_fused() {
              S, P.n_ops, P.n_vregs, P.n_prefetch, alg);
     cur.text = hdr;
     for (size_t i = 0; i < txt.size(); i++) cur.text += "    " + txt[i] + "\n";
+    {   // the lowered program as the kernel sees it (physical shared-memory slots, prefetch flags): "op<code>:..." per op
+        std::string m = "    lowered:";
+        for (int i = 0; i < P.n_ops; i++) {
+            const Op& o = P.ops[i];
+            char b[96];
+            int k = snprintf(b, sizeof b, " %d", (int)o.code);
+            if (op_reads_vreg_field(o.code) || o.code == OP_SAVEV) k += snprintf(b + k, sizeof b - k, ":v%d", o.vreg == 0xFF ? -1 : (int)o.vreg);
+            for (int q = 0; q < 3; q++)
+                if (o.pflags & (1 << q)) k += snprintf(b + k, sizeof b - k, ":p%d=v%d", q, (int)o.pv[q]);
+            if (o.code == OP_LOADG || o.code == OP_ADDG || o.code == OP_COPYG || o.code == OP_STOREG) k += snprintf(b + k, sizeof b - k, ":g%d%s", (int)o.buf, o.aux ? "*" : "");
+            m += b;
+        }
+        cur.text += m + "\n";
+    }
     steps.push_back(cur);
     cur = Step();
     ops.clear();
@@ -793,7 +824,7 @@ int Lowerer::lower() {
                         op.code = OP_DISTORT;
                         op.mode = (uint8_t)nd.enums[0];
                         ctl_param(op, 0, 0);
-                        set_const_div(op, 0, 1, nd.f32[0]);
+                        set_const_div(op, 0, 1, nd.f32[0], e.plan_only);
                         snprintf(b, sizeof b, "acc = distort[%s](acc, %g)", nt.enums[0].variants[nd.enums[0]], nd.f32[0]);
                         break;
                     case T_OVERDRIVE:
@@ -860,11 +891,11 @@ int ensure_resources(dspb_engine* e) {
     for (auto& np : e->nodes) {
         Node& n = *np;
         if (is_stateful(n.type) && !n.state.p) {
-            int r = n.state.alloc((size_t)C * 16, true);
+            int r = n.state.alloc((size_t)C * 16, true, e->plan_only);
             if (r) return r;
         }
         if (n.type == T_REVERB && (n.ring_dirty || !n.ring.p)) {
-            int r = n.ring.alloc((size_t)C * n.D * 4, true);  // "full of zeros": reverb.rs:63-68
+            int r = n.ring.alloc((size_t)C * n.D * 4, true, e->plan_only);  // "full of zeros": reverb.rs:63-68
             if (r) return r;
             n.pos = 0;
             n.ring_dirty = false;
@@ -874,20 +905,20 @@ int ensure_resources(dspb_engine* e) {
             const int F = 1 << e->cfg.fir_fft_log2;
             n.hist_pad = (int)round_up(std::max(N - 1, 4), 4);
             for (auto& u : n.U) {
-                int r = u.alloc((size_t)C * (n.hist_pad + maxn) * 4, true);
+                int r = u.alloc((size_t)C * (n.hist_pad + maxn) * 4, true, e->plan_only);
                 if (r) return r;
             }
-            int r = n.Y.alloc((size_t)C * maxn * 4, false);
+            int r = n.Y.alloc((size_t)C * maxn * 4, false, e->plan_only);
             if (r) return r;
-            r = n.H.alloc((size_t)F * 16, false);  // two spectrum tables (scalar-kernel order, packed-kernel order)
+            r = n.H.alloc((size_t)F * 16, false, e->plan_only);  // two spectrum tables (scalar-kernel order, packed-kernel order)
             if (r) return r;
-            r = n.taps_dev.alloc((size_t)N * 8, false);
+            r = n.taps_dev.alloc((size_t)N * 8, false, e->plan_only);
             if (r) return r;
             const bool toep = e->cfg.fir_mode == FIR_TOEPLITZ && N <= fir_toeplitz_max_taps();
             if (toep) {
-                r = n.toep_tiles.alloc(fir_toeplitz_tiles_bytes(N), false);
+                r = n.toep_tiles.alloc(fir_toeplitz_tiles_bytes(N), false, e->plan_only);
                 if (r) return r;
-                r = n.toep_split.alloc(fir_toeplitz_split_bytes(N, C, maxn), true);  // rows beyond C stay zero
+                r = n.toep_split.alloc(fir_toeplitz_split_bytes(N, C, maxn), true, e->plan_only);  // rows beyond C stay zero
                 if (r) return r;
             }
             if (!e->plan_only) {
@@ -918,7 +949,7 @@ int lower_graph(dspb_engine* e) {
     e->steps = std::move(L.steps);
     while ((int)e->scratch.size() < L.n_scratch) {
         auto b = std::make_unique<DevBuf>();
-        r = b->alloc((size_t)e->cfg.channels * e->cfg.max_samples * 4, false);
+        r = b->alloc((size_t)e->cfg.channels * e->cfg.max_samples * 4, false, e->plan_only);
         if (r) return r;
         e->scratch.push_back(std::move(b));
     }
@@ -1091,7 +1122,6 @@ int dspb_engine_create(const dspb_config* cfg, dspb_engine** out) {
         CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
         if (prop.major < 10) return fail(DSPB_ERR_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name, prop.major, prop.minor);
     }
-    g_plan_only = plan_only;
     auto* e = new dspb_engine();
     e->plan_only = plan_only;
     e->cfg = *cfg;
@@ -1216,7 +1246,6 @@ int dspb_link(dspb_engine* e, int64_t src_node, const char* out_port, int64_t ds
 
 int dspb_compile(dspb_engine* e) {
     if (!e) return fail(DSPB_ERR_INVALID, "null engine");
-    g_plan_only = e->plan_only;
     if (!e->plan_only) CUDA_TRY(cudaSetDevice(e->cfg.device));
     int r = topo_sort(e);
     if (r) return r;
@@ -1240,7 +1269,6 @@ int dspb_reset_state(dspb_engine* e) {
 int dspb_process(dspb_engine* e, const float* const* inputs, float* const* outputs, int64_t n, int mem_kind, void* stream) {
     if (!e) return fail(DSPB_ERR_INVALID, "null engine");
     if (e->plan_only) return fail(DSPB_ERR_CUDA, "planning-only engine (device -1) cannot process: there is no CPU fallback");
-    g_plan_only = false;
     CUDA_TRY(cudaSetDevice(e->cfg.device));
     int r = check_ready(e, n);
     if (r) return r;
@@ -1301,13 +1329,13 @@ int dspb_process(dspb_engine* e, const float* const* inputs, float* const* outpu
     }
     while (e->h_in.size() < n_in) {
         auto b = std::make_unique<DevBuf>();
-        r = b->alloc((size_t)C * e->cfg.max_samples * 4, false);
+        r = b->alloc((size_t)C * e->cfg.max_samples * 4, false, e->plan_only);
         if (r) return r;
         e->h_in.push_back(std::move(b));
     }
     while (e->h_out.size() < n_out) {
         auto b = std::make_unique<DevBuf>();
-        r = b->alloc((size_t)C * e->cfg.max_samples * 4, false);
+        r = b->alloc((size_t)C * e->cfg.max_samples * 4, false, e->plan_only);
         if (r) return r;
         e->h_out.push_back(std::move(b));
     }
@@ -1529,19 +1557,31 @@ int dspb_load_graph_json(dspb_engine* e, const char* text) {
     const jsonmin::Value* links = doc.get("links");
     if (!nodes || !nodes->is_array() || !links || !links->is_array()) return fail(DSPB_ERR_PARSE, "graph JSON: need 'nodes' and 'links' arrays");
     std::map<std::pair<int64_t, int64_t>, std::pair<std::string, bool>> port_names;  // (node, PortId) -> (name, is_output)
+    // GUI-only sinks (nodes/mod.rs:111-122: oscilloscope, spectrogram, pitch read-out): no output port, no effect on any
+    // audio value.  They are dropped together with the links into them, so a graph saved with a scope attached loads.
+    std::set<int64_t> dropped_sinks;
+    auto is_gui_sink = [](const std::string& t) { return t == "wave_view" || t == "spectrogram" || t == "pitch"; };
     for (const auto& nv : nodes->arr) {
         const jsonmin::Value* id = nv.get("id");
         const jsonmin::Value* tn = nv.get("typename");
         const jsonmin::Value* cfg = nv.get("cfg");
         if (!id || !id->is_number() || !tn || !tn->is_string() || !cfg || !cfg->is_object()) return fail(DSPB_ERR_PARSE, "graph JSON: malformed node entry");
         const int64_t nid = (int64_t)id->num;
+        if (is_gui_sink(tn->str)) { dropped_sinks.insert(nid); continue; }
+        if (tn->str == "muff")
+            return fail(DSPB_ERR_UNKNOWN_NODE, "typename 'muff' (nodes/muff.rs) is not supported: its arithmetic lives in the private "
+                                               "GPL crate dsp-stuff-gpl@170f168, which is not part of the reference tree");
         int r = dspb_node_add(e, tn->str.c_str(), nid);
         if (r) return r;
         Node& n = *e->nodes.back();
+        const bool terminal = n.type == T_INPUT || n.type == T_OUTPUT;
         for (const auto& kv : cfg->obj) {
             const std::string& k = kv.first;
             const jsonmin::Value& v = kv.second;
             if (k == "id" || k == "file_name") continue;
+            // InputConfig / OutputConfig (nodes/input.rs:33-38, nodes/output.rs:33-38): the cpal host and device names.
+            // The engine's terminals bind to dspb_process buffers instead of audio devices.
+            if (terminal && (k == "selected_host" || k == "selected_device")) continue;
             if (k == "inputs" || k == "outputs") {
                 if (!v.is_object()) return fail(DSPB_ERR_PARSE, "graph JSON: '%s' must be a name -> PortId map", k.c_str());
                 for (const auto& pv : v.obj) port_names[{nid, (int64_t)pv.second.num}] = {pv.first, k == "outputs"};
@@ -1572,6 +1612,7 @@ int dspb_load_graph_json(dspb_engine* e, const char* text) {
             return fail(DSPB_ERR_PARSE, "graph JSON: malformed link entry");
         const int64_t sn = (int64_t)lhs->arr[0].num, sp = (int64_t)lhs->arr[1].num;
         const int64_t dn = (int64_t)rhs->arr[0].num, dp = (int64_t)rhs->arr[1].num;
+        if (dropped_sinks.count(dn)) continue;  // link into a GUI sink
         auto a = port_names.find({sn, sp});
         auto b = port_names.find({dn, dp});
         if (a == port_names.end() || b == port_names.end() || !a->second.second || b->second.second)

@@ -10,6 +10,8 @@
 // with taps[0] (a running prefix sum of x[i]*taps[i]), not zero-padded convolution.
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include "plan.h"
 
 namespace dspb {
@@ -62,11 +64,12 @@ int launch_fir_direct(const FirPlan& fp, const float* U, int64_t u_stride, float
                       int64_t T, int64_t started, int64_t n_begin, int64_t n_end, cudaStream_t st) {
     const int N = fp.n_taps;
     const size_t smem = (size_t)(kDirectTile + N - 1) * 4;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    static std::atomic<size_t> configured_dev[kMaxDevices];  // per device: the opt-in is a per-device function attribute
+    std::atomic<size_t>& configured = configured_dev[current_device_slot()];
+    if (smem > 48 * 1024 && smem > configured.load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(fir_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        configured = smem;
+        configured.store(smem, std::memory_order_release);
     }
     if (n_end <= n_begin) return 0;
     const int C = c_end - c_begin;

@@ -15,7 +15,9 @@
 // the 1e-5 / -100 dBFS parity bar against the reference's f64 accumulation (tests/test_gpu_fir.py).
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cmath>
+#include <mutex>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -698,14 +700,14 @@ fir_spectrum_kernel(const double* __restrict__ taps_rev, int N, const double2* _
 struct Tables {
     float2* Wf = nullptr;
     double2* Wd = nullptr;
-    int device = -1;
 };
-Tables g_tab;
+Tables g_tab_dev[kMaxDevices];  // twiddle tables live in one device's memory: one set per device, built once
+std::mutex g_tab_mu;
+#define g_tab g_tab_dev[current_device_slot()]
 
 int ensure_tables() {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (g_tab.Wf && g_tab.device == dev) return 0;
+    std::lock_guard<std::mutex> lk(g_tab_mu);
+    if (g_tab.Wf) return 0;
     std::vector<float2> wf(kF);
     std::vector<double2> wd(kF);
     for (int k = 0; k < kF; k++) {
@@ -718,7 +720,6 @@ int ensure_tables() {
     if ((e = cudaMalloc(&g_tab.Wd, kF * sizeof(double2))) != cudaSuccess) return (int)e;
     if ((e = cudaMemcpy(g_tab.Wf, wf.data(), kF * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
     if ((e = cudaMemcpy(g_tab.Wd, wd.data(), kF * sizeof(double2), cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
-    g_tab.device = dev;
     return 0;
 }
 
@@ -734,12 +735,13 @@ int launch_fir_fft(const FirPlan& fp, const float* U, int64_t u_stride, float* Y
     int rc = ensure_tables();
     if (rc) return rc;
     if (fp.mode == FIR_FFT_PACKED) {  // opt-in: measured 5 % slower than the scalar kernel (see the comment above VF)
-        static bool configured2 = false;
+        static std::atomic<bool> configured2_dev[kMaxDevices];
+        std::atomic<bool>& configured2 = configured2_dev[current_device_slot()];
         const int smem2 = (kH2 + kCoarse + kFine) * (int)sizeof(float4);
-        if (!configured2) {
+        if (!configured2.load(std::memory_order_acquire)) {
             cudaError_t e = cudaFuncSetAttribute(fir_fft_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
             if (e != cudaSuccess) return (int)e;
-            configured2 = true;
+            configured2.store(true, std::memory_order_release);
         }
         const long long n_seg2 = (T + kH2 - 1) / kH2;
         const int pairs2 = (c_end - c_begin + 1) / 2;
@@ -752,12 +754,13 @@ int launch_fir_fft(const FirPlan& fp, const float* U, int64_t u_stride, float* Y
         }
         return (int)cudaGetLastError();
     }
-    static bool configured = false;
+    static std::atomic<bool> configured_dev[kMaxDevices];
+    std::atomic<bool>& configured = configured_dev[current_device_slot()];
     const int smem = (kPadded + kCoarse + kFine) * (int)sizeof(float2);
-    if (!configured) {
+    if (!configured.load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(fir_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured.store(true, std::memory_order_release);
     }
     const int Ne = effective_taps(fp.n_taps);
     const int V = kF - Ne + 1;

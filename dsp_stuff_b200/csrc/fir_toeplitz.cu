@@ -29,6 +29,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include <cstdint>
 
 #include "plan.h"
@@ -297,11 +299,12 @@ int launch_fir_toeplitz(const FirPlan& fp, const float* U, int64_t u_stride, flo
                         int64_t T, cudaStream_t st, int* n_launches) {
     if (!fp.toep_tiles || !fp.toep_split || fp.n_taps > fir_toeplitz_max_taps()) return (int)cudaErrorInvalidValue;
     if ((u_stride & 3) || (fp.hist_pad & 3)) return (int)cudaErrorInvalidValue;  // 16-byte aligned row chunks
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<bool> configured_dev[kMaxDevices];  // per device: the opt-in is a per-device function attribute
+    std::atomic<bool>& configured = configured_dev[current_device_slot()];
+    if (!configured.load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(fir_toeplitz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured.store(true, std::memory_order_release);
     }
     const int dmax = toep_dmax(fp.n_taps), nK = toep_nK(fp.n_taps);
     const int n_tiles = (int)((T + kTM - 1) / kTM);

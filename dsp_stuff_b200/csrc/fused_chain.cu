@@ -20,8 +20,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #include "exact_math.cuh"
 #include "plan.h"
@@ -1437,11 +1439,12 @@ bool ws2_rec_indices(const Program& p, int* r1, int* r2) {
 template <int G, bool XR>
 int launch_ws2(const Program& prog, int c_begin, int c_end, int64_t T, int r1, int r2, cudaStream_t st) {
     const int smem = Ws2Smem<G>::bytes;
-    static bool configured = false;
-    if (!configured) {
+    static std::atomic<bool> configured_dev[kMaxDevices];
+    std::atomic<bool>& configured = configured_dev[current_device_slot()];
+    if (!configured.load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(fused_kernel_ws2<G, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
+        configured.store(true, std::memory_order_release);
     }
     const int n_cta = (c_end - c_begin + G - 1) / G;
     fused_kernel_ws2<G, XR><<<n_cta, XR ? kXrLaunchThreads : kWs2LaunchThreads, smem, st>>>(prog, c_begin, c_end, (long long)T, r1, r2);
@@ -1465,8 +1468,7 @@ int ws_smem_bytes(const Program& prog, int G) {
 }
 // does op read / write shared-memory vreg v?
 bool op_reads_vreg(const Op& op, int v) {
-    const int c = op.code;
-    if ((c == OP_LOADV || c == OP_ADDV || c == OP_COPYV || c == OP_ADD || c == OP_MIX || c == OP_GATE) && op.vreg == v) return true;
+    if (op_reads_vreg_field(op.code) && op.vreg == v) return true;
     for (int i = 0; i < 3; i++)
         if ((op.pflags & (1 << i)) && op.pv[i] == v) return true;
     return false;
@@ -1502,18 +1504,20 @@ int ws_rec_index(const Program& p) {
 template <int G, class Chain, bool XR>
 int launch_ws(const Program& prog, int c_begin, int c_end, int64_t T, int rec_index, cudaStream_t st) {
     const int smem = ws_smem_bytes(prog, G);
-    static int configured = -1;
-    static int regs = 0, n_sm = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(fused_kernel_ws<G, Chain, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
-        cudaFuncAttributes fa;
-        if (cudaFuncGetAttributes(&fa, fused_kernel_ws<G, Chain, XR>) == cudaSuccess) regs = fa.numRegs;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (n_sm <= 0) n_sm = 148;
+    struct DevCfg { std::mutex mu; int configured = -1; int regs = 0; };
+    static DevCfg cfg_dev[kMaxDevices];
+    DevCfg& dc = cfg_dev[current_device_slot()];
+    int regs;
+    {
+        std::lock_guard<std::mutex> lk(dc.mu);
+        if (smem > dc.configured) {
+            cudaError_t e = cudaFuncSetAttribute(fused_kernel_ws<G, Chain, XR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return (int)e;
+            dc.configured = smem;
+            cudaFuncAttributes fa;
+            if (cudaFuncGetAttributes(&fa, fused_kernel_ws<G, Chain, XR>) == cudaSuccess) dc.regs = fa.numRegs;
+        }
+        regs = dc.regs;
     }
     if (XR) {
         const int n_cta = (c_end - c_begin + G - 1) / G;
@@ -1566,18 +1570,24 @@ bool chain_matches(const Program& p) {
 template <int G, class Chain>
 int launch_gc(const Program& prog, int c_begin, int c_end, int64_t T, int n_states, cudaStream_t st) {
     const int smem = fused_smem_bytes(prog, G);
-    static int configured = -1;
-    static int n_sm = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(fused_kernel<G, Chain>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return (int)e;
-        configured = smem;
-    }
-    if (!n_sm) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        if (n_sm <= 0) n_sm = 148;
+    struct DevCfg { std::mutex mu; int configured = -1; int n_sm = 0; };
+    static DevCfg cfg_dev[kMaxDevices];
+    DevCfg& dc = cfg_dev[current_device_slot()];
+    int n_sm;
+    {
+        std::lock_guard<std::mutex> lk(dc.mu);
+        if (smem > dc.configured) {
+            cudaError_t e = cudaFuncSetAttribute(fused_kernel<G, Chain>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return (int)e;
+            dc.configured = smem;
+        }
+        if (!dc.n_sm) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&dc.n_sm, cudaDevAttrMultiProcessorCount, dev);
+            if (dc.n_sm <= 0) dc.n_sm = 148;
+        }
+        n_sm = dc.n_sm;
     }
     const int n_cta = (c_end - c_begin + G - 1) / G;
     fused_kernel<G, Chain><<<n_cta, kThreads, smem, st>>>(prog, c_begin, c_end, (long long)T, n_states, n_sm);

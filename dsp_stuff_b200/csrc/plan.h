@@ -14,6 +14,16 @@
 
 namespace dspb {
 
+// Launch-time caches (cudaFuncSetAttribute opt-ins, SM counts, register counts, twiddle tables) are PER DEVICE:
+// one process may hold engines on several GPUs (include/dspb200.h), and a function attribute set on device 0 says
+// nothing about device 1.  Every such cache is an array indexed by the current device ordinal.
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d < 0 || d >= kMaxDevices) ? 0 : d;
+}
+
 constexpr int kThreads = 512;       // elementwise threads per CTA
 constexpr int kChunk = 8;           // consecutive samples per thread (8: twice the warps of 16 for latency hiding)
 constexpr int kTile = kThreads * kChunk;  // 4096 samples per CTA tile
@@ -68,6 +78,11 @@ struct Op {
     float p[6];       // p[4], p[5]: fan-in divisor and its reciprocal when pre & 2
     float a2;         // biquad: a2 (p[0..3] = b0, b1, b2, a1)
 };
+
+// Does an op of this code read the shared-memory vreg named by Op::vreg?  (SAVEV writes it; parameter tiles are in pv[].)
+inline constexpr bool op_reads_vreg_field(int code) {
+    return code == OP_LOADV || code == OP_ADDV || code == OP_COPYV || code == OP_ADD || code == OP_MIX || code == OP_GATE;
+}
 
 struct BufDesc {       // a [C x n] f32 array in global memory
     float* base;       // element (channel 0, sample 0 of this call)

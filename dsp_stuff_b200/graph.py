@@ -38,6 +38,9 @@ NODE_PORTS: Dict[str, Tuple[Tuple[str, ...], Tuple[str, ...]]] = {
     "output": (("in",), ()),
 }
 
+# GUI-only sink typenames (nodes/mod.rs:111-122): restored by the reference, irrelevant to any audio value.
+GUI_SINKS = ("wave_view", "spectrogram", "pitch")
+
 # Saved enum fields per typename (serialised as the variant name string).
 ENUM_FIELDS = {
     "distort": ("mode",),
@@ -131,8 +134,12 @@ class GraphSpec:
         doc = json.loads(text)
         g = GraphSpec()
         pid_name: Dict[Tuple[int, int], Tuple[str, bool]] = {}
+        dropped = set()
         for nd in doc["nodes"]:
             typename = nd["typename"]
+            if typename in GUI_SINKS:  # oscilloscope / spectrogram / pitch read-out: no output port, dropped with their links
+                dropped.add(int(nd["id"]))
+                continue
             if typename not in NODE_PORTS:
                 raise KeyError(f"unknown typename {typename!r}")  # reference panics: runtime.rs:634-637
             cfg = nd["cfg"]
@@ -144,6 +151,8 @@ class GraphSpec:
             for k, v in cfg.items():
                 if k in ("id", "inputs", "outputs", "file_name"):
                     continue
+                if typename in ("input", "output") and k in ("selected_host", "selected_device"):
+                    continue  # cpal host / device names (nodes/input.rs:33-38, nodes/output.rs:33-38)
                 if k == "taps":
                     spec.taps = [float(t) for t in v]
                 elif isinstance(v, str):
@@ -153,5 +162,7 @@ class GraphSpec:
             g.nodes.append(spec)
         for l in doc["links"]:
             (sn, sp), (dn, dp) = l["lhs"], l["rhs"]
+            if int(dn) in dropped:
+                continue
             g.links.append((int(sn), pid_name[(int(sn), int(sp))][0], int(dn), pid_name[(int(dn), int(dp))][0]))
         return g

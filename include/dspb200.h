@@ -106,12 +106,19 @@ int dspb_node_set_impulse_response(dspb_engine* e, int64_t node_id, const double
 /* Replaces: UiContext::add_link (runtime.rs:125-134): lhs = (producer node, output port),
  * rhs = (consumer node, input port); ports by name (node.rs:87-89).  Several links may leave one
  * output port (fan-out, node.rs:321-325) or enter one input port (fan-in, averaged by
- * collect_and_average, node.rs:162-194, summed in link-creation order). */
+ * collect_and_average, node.rs:162-194).  The engine sums a port's links in link-creation order; the reference
+ * iterates a HashSet<LinkId> (runtime.rs:38-39), i.e. in unspecified order, so with three or more links into one
+ * port the sum is reproducible against the reference only up to f32 rounding of the addition order (one or two
+ * links: order-independent, bit-exact). */
 int dspb_link(dspb_engine* e, int64_t src_node, const char* out_port, int64_t dst_node, const char* in_port);
 
 /* Replaces: UiContext::restore_config (runtime.rs:94-123) for the saved-graph JSON
  * DSPConfig{nodes:[{id,typename,position,cfg}],links:[{lhs:[node,port],rhs:[node,port]}]}
- * (runtime.rs:44-48, 560-564, 606-612).  Adds to an empty engine. */
+ * (runtime.rs:44-48, 560-564, 606-612).  Adds to an empty engine.  `input` / `output` entries keep their
+ * cpal fields selected_host / selected_device (nodes/input.rs:33-38, nodes/output.rs:33-38), which are ignored:
+ * terminals bind to dspb_process buffers.  GUI-only sinks (wave_view, spectrogram, pitch: nodes/mod.rs:111-122) are
+ * dropped together with the links into them.  `muff` (private GPL crate, source unavailable) and any other unknown
+ * typename fail with DSPB_ERR_UNKNOWN_NODE, where the reference panics (runtime.rs:634-637). */
 int dspb_load_graph_json(dspb_engine* e, const char* json_utf8);
 
 /* Replaces: UiContext::update_all / NodeInstance::start (runtime.rs:136-151, 646-732): builds the

@@ -185,3 +185,91 @@ def test_saved_graph_json_lowers_in_planning_mode(lib, name, expect):
         Engine(4, device=-1).load_graph_json('{"nodes": [{"id": 0, "typename": "no_such_node", "position": [0, 0], "cfg": {}}], "links": []}')
     with pytest.raises(EngineError):
         Engine(4, device=-1).load_graph_json('{"nodes": [')
+
+
+@pytest.mark.parametrize("name,expect,absent", [
+    ("ref_shape_pedalboard", ["gain#3", "distort[SoftClip]", "DF1(", "high_pass(acc; ratio=0.75)", "D=12288", "fir step: fir#13, 16 taps"],
+     ["wave_view", "spectrogram", "pitch"]),
+    ("ref_shape_fir_default", ["fir step: fir#5, 1 taps", "signal_gen[Triangle](amp=0.25, freq=440)", "mix#7"], []),
+])
+def test_reference_shaped_saved_graph_loads_in_planning_mode(lib, name, expect, absent):
+    """dspb_load_graph_json on graphs written the way the reference's serde structs write them (Input / Output carry
+    selected_host / selected_device, GUI sinks are attached): tests/golden/ref_shape_*.json are hand-written."""
+    from dsp_stuff_b200.engine import Engine
+
+    text = open(os.path.join(ROOT, "tests", "golden", f"{name}.json")).read()
+    e = Engine(64, block=128, max_samples=128 * 8, device=-1)
+    e.load_graph_json(text)
+    plan = e.describe_plan()
+    for s in expect:
+        assert s in plan, (s, plan)
+    for s in absent:
+        assert s not in plan, (s, plan)
+
+
+def test_saved_graph_with_muff_is_an_unknown_node_error(lib):
+    import json
+
+    from dsp_stuff_b200.engine import Engine, EngineError
+
+    doc = json.loads(open(os.path.join(ROOT, "tests", "golden", "ref_shape_fir_default.json")).read())
+    doc["nodes"].append({"id": 40, "typename": "muff", "position": [0.0, 0.0],
+                         "cfg": {"id": 40, "inputs": {"in": 41}, "outputs": {"out": 42}, "toan": 0.5, "level": 0.5, "sustain": 0.5}})
+    with pytest.raises(EngineError) as ei:
+        Engine(4, device=-1).load_graph_json(json.dumps(doc))
+    assert ei.value.code == -2 and "muff" in str(ei.value)
+
+
+def _lowered(plan):
+    """'lowered:' lines of describe_plan(): per fused step the ops as the kernel sees them, [(code, attrs...)]"""
+    out = []
+    for line in plan.splitlines():
+        if line.strip().startswith("lowered:"):
+            out.append([tok.split(":") for tok in line.split("lowered:")[1].split()])
+    return out
+
+
+OP_LOADG, OP_SAVEV, OP_STOREG, OP_GATE = "3", "10", "11", "25"   # csrc/plan.h OpCode
+
+
+@pytest.mark.parametrize("front", ["gain", "biquad", "distort"])
+def test_gate_operand_is_remapped_to_an_allocated_vreg(lib, front):
+    """the gate's saved input must be renamed to its physical shared-memory slot like every other vreg
+    operand (it used to keep its virtual id, i.e. read a slot that was never allocated once a node sat in front)."""
+    import re
+
+    from dsp_stuff_b200 import GraphSpec
+    from dsp_stuff_b200.engine import Engine
+
+    g = (GraphSpec().node(10, "input").node(11, "output").node(0, front).node(1, "gate", threshold=0.3, release=40.0)
+         .link(10, "out", 0, "in").link(0, "out", 1, "in").link(1, "out", 11, "in"))
+    e = Engine(64, device=-1)
+    g.apply(e)
+    plan = e.describe_plan()
+    n_vregs = int(re.search(r"(\d+) smem vregs", plan).group(1))
+    ops = _lowered(plan)[0]
+    gates = [o for o in ops if o[0] == OP_GATE]
+    saves = {o[1] for o in ops if o[0] == OP_SAVEV}
+    assert len(gates) == 1 and n_vregs >= 1
+    assert int(gates[0][1][1:]) < n_vregs and gates[0][1] in saves, (plan, ops)
+
+
+def test_value_spilled_and_reused_in_one_step_is_not_prefetched(lib):
+    """signal_gen -> {fir, gain}: the generator's value is stored to scratch for the FIR step and re-read by
+    the gain in the same kernel; a one-tile-ahead register prefetch of that buffer would read the previous call's data."""
+    from dsp_stuff_b200 import GraphSpec
+    from dsp_stuff_b200.engine import Engine
+
+    g = (GraphSpec().node(11, "output").node(12, "output").node(0, "signal_gen", frequency=440.0)
+         .node(1, "fir", taps=[0.5, 0.25, 0.125]).node(2, "gain", level=2.0)
+         .link(0, "out", 1, "in").link(0, "out", 2, "in").link(1, "out", 11, "in").link(2, "out", 12, "in"))
+    e = Engine(64, device=-1)
+    g.apply(e)
+    steps = _lowered(e.describe_plan())
+    for ops in steps:
+        stored = set()
+        for o in ops:
+            if o[0] == OP_STOREG:
+                stored.add(o[1].rstrip("*"))
+            if o[0] == OP_LOADG and o[1].rstrip("*") in stored:
+                assert not o[1].endswith("*"), ("prefetched although stored earlier in the same program", ops)
