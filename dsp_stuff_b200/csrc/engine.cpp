@@ -144,11 +144,14 @@ struct Node {
     DevBuf state;  // [C x 4] f32
     // fir
     std::vector<double> taps{1.0};  // reversed, nodes/fir.rs:61
-    DevBuf U[2];                    // [C x (hist_pad + max_samples)] input incl. history, double-buffered
+    DevBuf U;                       // [C x u_ring] input rings: a call's sample i sits at slot (u_pos + i) mod u_ring, the
+                                    // previous hist_pad samples right behind it -- history carries over without a copy
+    int u_ring = 0, u_pos = 0;      // u_ring = round_up(hist_pad + max_samples, 128)
     DevBuf Y;                       // [C x max_samples]
+    std::vector<std::unique_ptr<DevBuf>> fft_work;  // persistent FFT kernel: work counter + per-CTA scratch, one per launch lane
     DevBuf H, taps_dev;
     DevBuf toep_tiles, toep_split;  // FIR_TOEPLITZ: Toeplitz tiles of the taps, hi/lo bf16 split of U
-    int hist_pad = 0, cur_u = 0;
+    int hist_pad = 0;
     int64_t started = 0;            // samples this node has consumed since reset
     bool fir_dirty = true;
 };
@@ -286,10 +289,9 @@ int clear_node_state(dspb_engine* e, Node& n) {
     if (n.state.p) CUDA_TRY(cudaMemset(n.state.p, 0, n.state.bytes));
     if (n.ring.p) CUDA_TRY(cudaMemset(n.ring.p, 0, n.ring.bytes));
     n.pos = 0;
-    for (auto& u : n.U)
-        if (u.p) CUDA_TRY(cudaMemset(u.p, 0, u.bytes));
+    if (n.U.p) CUDA_TRY(cudaMemset(n.U.p, 0, n.U.bytes));
     n.started = 0;
-    n.cur_u = 0;
+    n.u_pos = 0;
     (void)e;
     return DSPB_OK;
 }
@@ -732,7 +734,8 @@ int Lowerer::lower() {
                 char b[200];
                 if (e.cfg.fir_mode == FIR_FFT || e.cfg.fir_mode == FIR_FFT_PACKED)
                     snprintf(b, sizeof b, "fir step: %s, %zu taps, overlap-save FFT 2^%d%s, two channels per transform, alg_bytes=8\n", tag.c_str(),
-                             nd.taps.size(), e.cfg.fir_fft_log2, e.cfg.fir_mode == FIR_FFT_PACKED ? " (packed f32x2 variant)" : "");
+                             nd.taps.size(), e.cfg.fir_fft_log2,
+                             e.cfg.fir_mode == FIR_FFT_PACKED ? " (packed f32x2 variant)" : " (+ 2^14 double segments as two sub-transforms, persistent CTAs)");
                 else if (e.cfg.fir_mode == FIR_TOEPLITZ)
                     snprintf(b, sizeof b, "fir step: %s, %zu taps, Toeplitz-tiled tcgen05 GEMM 128x256x32, split bf16 (3 MMAs per K step), alg_bytes=8\n",
                              tag.c_str(), nd.taps.size());
@@ -904,14 +907,15 @@ int ensure_resources(dspb_engine* e) {
             const int N = (int)n.taps.size();
             const int F = 1 << e->cfg.fir_fft_log2;
             n.hist_pad = (int)round_up(std::max(N - 1, 4), 4);
-            for (auto& u : n.U) {
-                int r = u.alloc((size_t)C * (n.hist_pad + maxn) * 4, true, e->plan_only);
-                if (r) return r;
-            }
-            int r = n.Y.alloc((size_t)C * maxn * 4, false, e->plan_only);
+            if ((int64_t)n.hist_pad + maxn > (1ll << 30)) return fail(DSPB_ERR_INVALID, "max_samples too large for the FIR input ring");
+            n.u_ring = (int)round_up(n.hist_pad + maxn, 128);
+            int r = n.U.alloc((size_t)C * n.u_ring * 4, true, e->plan_only);
             if (r) return r;
-            r = n.H.alloc((size_t)F * 16, false, e->plan_only);  // two spectrum tables (scalar-kernel order, packed-kernel order)
+            r = n.Y.alloc((size_t)C * maxn * 4, false, e->plan_only);
             if (r) return r;
+            r = n.H.alloc(fir_fft_spectrum_bytes(), false, e->plan_only);  // every spectrum table of the FFT kernels
+            if (r) return r;
+            (void)F;
             r = n.taps_dev.alloc((size_t)N * 8, false, e->plan_only);
             if (r) return r;
             const bool toep = e->cfg.fir_mode == FIR_TOEPLITZ && N <= fir_toeplitz_max_taps();
@@ -933,7 +937,7 @@ int ensure_resources(dspb_engine* e) {
                 CUDA_TRY(cudaDeviceSynchronize());
             }
             n.started = 0;
-            n.cur_u = 0;
+            n.u_pos = 0;
             n.fir_dirty = false;
         }
     }
@@ -1006,7 +1010,8 @@ int topo_sort(dspb_engine* e) {
 }
 
 // Bind per-call pointers and launch every step for channels [c0, c1).
-int run_steps(dspb_engine* e, const float* const* d_in, float* const* d_out, int64_t n, int c0, int c1, cudaStream_t st) {
+// `lane`: index of the concurrent launch lane (device-pointer chunks run on their own streams), selects per-lane scratch.
+int run_steps(dspb_engine* e, const float* const* d_in, float* const* d_out, int64_t n, int c0, int c1, cudaStream_t st, int lane = 0) {
     int step_idx = -1;
     for (auto& s : e->steps) {
         step_idx++;
@@ -1021,14 +1026,18 @@ int run_steps(dspb_engine* e, const float* const* d_in, float* const* d_out, int
             Program& P = s.prog;
             for (size_t b = 0; b < s.binds.size(); b++) {
                 BufDesc& d = P.bufs[b];
+                d.ring_len = 0;
+                d.ring_pos = 0;
                 switch (s.binds[b].kind) {
                     case 0: d.base = const_cast<float*>(d_in[s.binds[b].idx]); d.row_stride = n; break;
                     case 1: d.base = d_out[s.binds[b].idx]; d.row_stride = n; break;
                     case 2: d.base = e->scratch[s.binds[b].idx]->p; d.row_stride = e->cfg.max_samples; break;
-                    case 3: {
+                    case 3: {  // FIR input ring
                         Node& f = *e->nodes[s.binds[b].idx];
-                        d.row_stride = f.hist_pad + e->cfg.max_samples;
-                        d.base = f.U[f.cur_u].p + f.hist_pad;
+                        d.row_stride = f.u_ring;
+                        d.base = f.U.p;
+                        d.ring_len = f.u_ring;
+                        d.ring_pos = f.u_pos;
                     } break;
                     case 4: {
                         Node& f = *e->nodes[s.binds[b].idx];
@@ -1062,19 +1071,25 @@ int run_steps(dspb_engine* e, const float* const* d_in, float* const* d_out, int
             fp.taps = reinterpret_cast<const double*>(f.taps_dev.p);
             fp.divisor = f.enums[0] == 0 ? 1.0f / (float)f.taps.size() : 1.0f;  // fir.rs:187-190
             fp.post_nf = s.fir_post_nf;
-            const int64_t us = f.hist_pad + e->cfg.max_samples;
+            fp.u_ring = f.u_ring;
+            fp.u_pos = f.u_pos;
+            // work area of the persistent FFT kernel: one per launch lane (lanes run concurrently on their own streams)
+            fp.fft_work = nullptr;
+            if (fp.mode == FIR_FFT) {
+                while ((int)f.fft_work.size() <= lane) {
+                    auto wb = std::make_unique<DevBuf>();
+                    int r = wb->alloc(fir_fft_work_bytes(), true, e->plan_only);
+                    if (r) return r;
+                    f.fft_work.push_back(std::move(wb));
+                }
+                fp.fft_work = f.fft_work[lane]->p;
+            }
             int nl = 0;
             float* yp = s.fir_out_term >= 0 ? d_out[s.fir_out_term] : f.Y.p;
             const int64_t ys = s.fir_out_term >= 0 ? n : e->cfg.max_samples;
-            int rc = launch_fir(fp, f.U[f.cur_u].p, us, yp, ys, c0, c1, n, f.started, st, &nl);
+            int rc = launch_fir(fp, f.U.p, f.u_ring, yp, ys, c0, c1, n, f.started, st, &nl);
             if (rc) return fail(DSPB_ERR_CUDA, "fir kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
             e->last_launches += nl;
-            // carry the last hist_pad samples into the other U buffer (front) for the next call
-            for (int c = c0; c < c1; c += 4096) {
-                const int cc = std::min(c1, c + 4096) - c;
-                CUDA_TRY(cudaMemcpy2DAsync(f.U[f.cur_u ^ 1].p + (size_t)c * us, us * 4, f.U[f.cur_u].p + (size_t)c * us + n, us * 4,
-                                           (size_t)f.hist_pad * 4, cc, cudaMemcpyDeviceToDevice, st));
-            }
         }
     }
     return DSPB_OK;
@@ -1084,7 +1099,7 @@ void advance_state(dspb_engine* e, int64_t n) {
     for (auto& np : e->nodes) {
         Node& nd = *np;
         if (nd.type == T_REVERB && nd.D > 0) nd.pos = (nd.pos + n) % nd.D;
-        if (nd.type == T_FIR) { nd.started += n; nd.cur_u ^= 1; }
+        if (nd.type == T_FIR) { nd.started += n; nd.u_pos = (int)((nd.u_pos + n) % nd.u_ring); }
     }
 }
 
@@ -1310,7 +1325,7 @@ int dspb_process(dspb_engine* e, const float* const* inputs, float* const* outpu
                 const int c0 = k * per, c1 = std::min(C, c0 + per);
                 if (c0 >= c1) break;
                 CUDA_TRY(cudaStreamWaitEvent(e->chunk_streams[k], e->chunk_events[chunks], 0));
-                r = run_steps(e, inputs, outputs, n, c0, c1, e->chunk_streams[k]);
+                r = run_steps(e, inputs, outputs, n, c0, c1, e->chunk_streams[k], k);
                 if (r) return r;
                 CUDA_TRY(cudaEventRecord(e->chunk_events[k], e->chunk_streams[k]));
                 CUDA_TRY(cudaStreamWaitEvent(cs, e->chunk_events[k], 0));

@@ -28,18 +28,18 @@ constexpr int kDirectTile = 256;
 
 // One thread per output sample; the CTA's input window lives in shared memory.
 __global__ void __launch_bounds__(kDirectTile)
-fir_direct_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, float* __restrict__ Y, long long y_stride,
+fir_direct_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, int u_ring, int u_pos, float* __restrict__ Y, long long y_stride,
                   const double* __restrict__ taps, int N, long long T, long long started, float divisor, float post_nf,
                   int c_begin, long long n_begin, long long n_end) {
     extern __shared__ float xw[];  // [kDirectTile + N - 1]
     const int ch = c_begin + blockIdx.y;
     const long long tile0 = n_begin + (long long)blockIdx.x * kDirectTile;
     const long long w0 = tile0 - (N - 1);  // call-relative index of xw[0]; >= -hist_pad
-    const float* row = U + (long long)ch * u_stride + hist_pad;
+    const float* row = U + (long long)ch * u_stride;  // a ring of u_ring samples, call sample n at slot (u_pos + n) mod u_ring
     const int W = kDirectTile + N - 1;
     for (int i = threadIdx.x; i < W; i += kDirectTile) {
         const long long n = w0 + i;
-        xw[i] = (n < T && n >= -(long long)hist_pad) ? row[n] : 0.0f;
+        xw[i] = (n < T && n >= -(long long)hist_pad) ? row[ring_slot(u_pos, (int)n, u_ring)] : 0.0f;
     }
     __syncthreads();
     const long long n = tile0 + threadIdx.x;
@@ -76,7 +76,7 @@ int launch_fir_direct(const FirPlan& fp, const float* U, int64_t u_stride, float
     const long long tiles = (n_end - n_begin + kDirectTile - 1) / kDirectTile;
     for (int c = 0; c < C; c += 65535) {  // gridDim.y limit
         dim3 grid((unsigned)tiles, (unsigned)std::min(65535, C - c));
-        fir_direct_kernel<<<grid, kDirectTile, smem, st>>>(U, u_stride, fp.hist_pad, Y, y_stride, fp.taps, N, T, started,
+        fir_direct_kernel<<<grid, kDirectTile, smem, st>>>(U, u_stride, fp.hist_pad, fp.u_ring, fp.u_pos, Y, y_stride, fp.taps, N, T, started,
                                                           fp.divisor, fp.post_nf, c_begin + c, n_begin, n_end);
     }
     return (int)cudaGetLastError();

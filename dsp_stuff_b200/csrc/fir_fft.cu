@@ -1,22 +1,34 @@
 // fir_fft.cu — overlap-save FFT convolution for the Fir node (nodes/fir.rs:179-225), sm_100a.
 //
-// One CTA convolves one segment of TWO channels at once: z = xA + i*xB, Z = FFT(z), Y = Z .* H,
-// y = IFFT(Y); because h is real, Re(y) = xA * h and Im(y) = xB * h.  F = 8192 complex points live in
-// (padded, bank-conflict-free) shared memory; the transform is decimation-in-frequency with radices
-// 8, 8, 8, 16 forward and the exact mirror (decimation-in-time, conjugate twiddles) backward, so the
-// forward output order is irrelevant: H is produced ONCE per tap set by running the very same forward
-// passes (in f64) on the zero-padded impulse response and is stored in that same order, pre-scaled
-// by 1/F.  The last forward pass, the spectrum product and the first inverse pass happen in
-// registers.  The first pass reads the input window straight from global memory and the last pass
-// writes the F-N+1 valid outputs straight back (coalesced 4-byte accesses: the window start is not
-// 16-byte aligned because N-1 is odd).
+// One 8192-point complex transform lives in (padded, bank-conflict-free) shared memory and carries TWO channels at
+// once: z = xA + i*xB, Z = FFT(z), Y = Z .* H, y = IFFT(Y); because h is real, Re(y) = xA * h and Im(y) = xB * h.
+// The transform is decimation-in-frequency with radices 8, 8, 8, 16 forward and the exact mirror (decimation-in-time,
+// conjugate twiddles) backward, so the forward output order is irrelevant: H is produced ONCE per tap set by running the
+// very same forward passes (in f64) on the zero-padded impulse response and is stored in that same order, pre-scaled.
+// The last forward pass, the spectrum product and the first inverse pass happen in registers.  The first pass reads the
+// input window straight from global memory and the last pass writes the valid outputs straight back.
 //
-// Accuracy: f32 butterflies, twiddles from an f64-computed table: ~1e-7 of the signal rms, inside
-// the 1e-5 / -100 dBFS parity bar against the reference's f64 accumulation (tests/test_gpu_fir.py).
+// Segments.  An 8192-point window ("F13") yields V13 = 8192 - (Ne-1) valid outputs -- half of it at 4096 taps.  A
+// 16384-point window ("F14") yields 16384 - (Ne-1) = three quarters, and it is computed with the SAME 64 KB of shared
+// memory as two 8192-point sub-transforms in sequence (one radix-2 decimation-in-frequency step in front):
+//     E[n] = z[n] + z[n+8192]               -> even bins:  e' = IFFT8192(FFT8192(E) .* H[2k])
+//     O[n] = (z[n] - z[n+8192]) W16384^n    -> odd bins:   o' = IFFT8192(FFT8192(O) .* H[2k+1])
+//     y[n] = e'[n] + W16384^-n o'[n],   y[n+8192] = e'[n] - W16384^-n o'[n]
+// e' is parked in a per-CTA scratch slot in global memory between the two halves (each thread reads back exactly
+// the values it wrote; the slots are reused item after item, so they stay L2-resident).  At 4096 taps one F14 item
+// costs ~2.25 F13 items and yields 3x the outputs: 25 % fewer instructions per output sample.
+//
+// The kernel is persistent (3 CTAs per SM, 256 threads): CTAs fetch work items (channel pair, segment) from an
+// atomic counter in segment-major order within a pair, so the overlapping windows of neighbouring segments meet in L2.
+// The input rows are rings (plan.h FirPlan::u_ring): a call's last N-1 samples are the next call's history in place.
+//
+// Accuracy: f32 butterflies, twiddles from an f64-computed table: ~2e-7 of the signal peak, inside the 1e-5 / -100 dBFS
+// parity bar against the reference's f64 accumulation (tests/test_gpu_fir.py).
 #include <cuda_runtime.h>
 
 #include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include <type_traits>
 #include <utility>
@@ -142,18 +154,25 @@ __device__ __forceinline__ void ifft_dit(C2<T> (&v)[R]) {
 __host__ __device__ constexpr int bitrev3(int s) { return ((s & 1) << 2) | (s & 2) | ((s >> 2) & 1); }
 __device__ __forceinline__ int pad(int p) { return p + (p >> 4); }
 
-// Twiddle source.  W[k] = exp(-2 pi i k / F) factorised as coarse[k >> 4] * fine[k & 15] (512 + 16
-// entries, 4.1 KB of shared memory instead of an L2-resident 64 KB table).
-constexpr int kCoarse = kF / 16, kFine = 16;
+// Twiddle source.  W16384^n = coarse[n >> 5] * fine[n & 31] with coarse[m] = exp(-2 pi i m / 512) (512 entries) and
+// fine[b] = exp(-2 pi i b / 16384) (32 entries): 4.3 KB of shared memory instead of an L2-resident table.  The
+// 8192-point passes index in units of W8192 = W16384^2: W8192^k = coarse[k >> 4] * fine[2 (k & 15)].
+constexpr int kCoarse = kF / 16, kFine = 32;
 template <typename T>
 struct Tw {
     const C2<T>* coarse;  // [512] exp(-2 pi i m / 512)
-    const C2<T>* fine;    // [16]  exp(-2 pi i b / 8192)
-    __device__ __forceinline__ C2<T> at(int k) const {
+    const C2<T>* fine;    // [32]  exp(-2 pi i b / 16384)
+    __device__ __forceinline__ C2<T> at(int k) const {   // W8192^k
         k &= kF - 1;
         const C2<T> c = coarse[k >> 4];
         if ((k & 15) == 0) return c;
-        return cmul(c, fine[k & 15]);
+        return cmul(c, fine[2 * (k & 15)]);
+    }
+    __device__ __forceinline__ C2<T> at2(int n) const {  // W16384^n
+        n &= 2 * kF - 1;
+        const C2<T> c = coarse[n >> 5];
+        if ((n & 31) == 0) return c;
+        return cmul(c, fine[n & 31]);
     }
 };
 // twiddles w^q, q = 1..7, from three look-ups (w, w^2, w^4) and four products.  STEP = F/M: every index is
@@ -180,9 +199,8 @@ __device__ __forceinline__ void twiddles8(const Tw<T>& W, int k1, C2<T> (&w)[8])
 }
 template <typename T, typename TG>
 __device__ __forceinline__ Tw<T> load_tables(C2<T>* sm, const TG* __restrict__ Wg, int t) {
-    // sm: [512 + 16]; Wg: the full F-entry table in global memory
-    for (int i = t; i < kCoarse; i += kNT) sm[i] = C2<T>{(T)Wg[16 * i].x, (T)Wg[16 * i].y};
-    if (t < kFine) sm[kCoarse + t] = C2<T>{(T)Wg[t].x, (T)Wg[t].y};
+    // sm: [512 + 32]; Wg: the compact table in global memory, same layout
+    for (int i = t; i < kCoarse + kFine; i += kNT) sm[i] = C2<T>{(T)Wg[i].x, (T)Wg[i].y};
     return Tw<T>{sm, sm + kCoarse};
 }
 
@@ -233,77 +251,104 @@ __device__ __forceinline__ void inv_pass8(C2<T>* a, const Tw<T>& W, int t) {
 }
 
 // ---- the convolution kernel --------------------------------------------------------------------------
-// Ne = effective tap count: N padded with zero taps so that Ne - 1 is a multiple of 4.  Then every window
-// start (s0 - (Ne-1), s0 a multiple of V = F - Ne + 1) and every output run is 16-byte aligned and the
-// first / last pass move two consecutive samples per 64-bit access.
-// post: optional epilogue "acc = 0.0 + y; acc /= post_nf" = the fan-in average of a sink fed only by this
-// node (node.rs:162-194, nodes/output.rs:223), so no separate kernel has to touch the output again.
-// (0.0 + y) / nf with Markstein's three-instruction sequence (exact_math.cuh: correctly rounded except in the
-// denormal / overflow fringes, where it is one ulp off -- far inside this path's 1e-5 tolerance) instead of the
-// ~10-instruction IEEE division: the division was 7 % of this kernel's issued instructions.
+// hist = Ne - 1, Ne = effective tap count: N padded with zero taps so that hist is a multiple of 4.  Then every window
+// start (s0 - hist, s0 a multiple of the valid length) and every output run is 16-byte aligned and the first / last pass
+// move two consecutive samples per 64-bit access.
+// post: optional epilogue "acc = 0.0 + y; acc /= post_nf" = the fan-in average of a sink fed only by this node
+// (node.rs:162-194, nodes/output.rs:223), so no separate kernel has to touch the output again.
+// (0.0 + y) / nf uses Markstein's three-instruction sequence (exact_math.cuh: correctly rounded except in the denormal /
+// overflow fringes, where it is one ulp off -- far inside this path's 1e-5 tolerance, and this path is never bit-exact
+// anyway: the warm-up samples that ARE bit-exact come from fir_direct_kernel, which divides with __fdiv_rn).
 __device__ __forceinline__ float div_nf(float y, float nf, float rnf) {
     const float a = __fadd_rn(0.0f, y);
     const float q0 = __fmul_rn(a, rnf);
     return __fmaf_rn(__fmaf_rn(-q0, nf, a), rnf, q0);
 }
 
-__global__ void __launch_bounds__(kNT, 3)
-fir_fft_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, float* __restrict__ Y, long long y_stride,
-               const float2* __restrict__ Hg, const float2* __restrict__ Wg, int Ne, long long T, float divisor, float post_nf,
-               int c_begin, int c_end) {
-    extern __shared__ float2 smem_f2[];
-    C2<float>* a = reinterpret_cast<C2<float>*>(smem_f2);
-    const int t = threadIdx.x;
-    const Tw<float> W = load_tables<float>(a + kPadded, Wg, t);
-    const C2<float>* H = reinterpret_cast<const C2<float>*>(Hg);
-    const int V = kF - Ne + 1;  // valid outputs per segment (multiple of 4)
-    const long long s0 = (long long)blockIdx.x * V;
-    const long long w0 = s0 - (Ne - 1);  // call-relative index of window sample 0 (>= -hist_pad), multiple of 4
-    const int chA = c_begin + 2 * blockIdx.y, chB = chA + 1;
-    const bool hasB = chB < c_end;
-    const float* rowA = U + (long long)chA * u_stride + hist_pad + w0;
-    const float* rowB = U + (long long)(hasB ? chB : chA) * u_stride + hist_pad + w0;
-    const long long lim = T - w0;  // window samples >= lim lie beyond this call's input: zeros
-    __syncthreads();               // twiddle tables visible
+struct FftArgs {
+    const float* U;        // [C x u_stride] input rings
+    long long u_stride;
+    int u_ring, u_pos;     // call sample i lives at slot (u_pos + i) mod u_ring
+    int hist;              // Ne - 1: window samples in front of a segment's first output (multiple of 4, <= 4096)
+    float* Y;
+    long long y_stride;
+    const float2* H13;     // spectrum of h for an 8192-point segment, transform order, scaled 1/8192
+    const float2* H14e;    // even / odd bins of the 16384-point spectrum, same order, scaled 1/16384
+    const float2* H14o;
+    const float2* Wg;      // compact twiddle table [512 + 32]
+    long long T;
+    float divisor, post_nf;
+    int c_begin, c_end;
+    int n14, n13;          // per channel pair: n14 double segments (V14 outputs each), then n13 single segments (V13 each)
+    int n_items;           // pairs * (n14 + n13)
+    unsigned* work;        // [0] next item, [1] CTAs done
+    float4* scratch;       // [gridDim.x][kF / 2] e' of the even half, in the last pass's own register order
+};
 
-    // forward pass 1 (M = F, radix 8): operands straight from global memory, two butterflies per step
-    {
-        constexpr int L = kF / 8;
+// MODE 0: plain 8192-point segment.  MODE 1 / 2: even- / odd-bin half of a 16384-point segment.
+// FAST (CTA-uniform): the whole window lies inside this call's samples and does not wrap around the ring, and
+// hist == 4096, so no load is predicated and the valid outputs are exactly the butterfly outputs r >= 4.
+template <int MODE, bool FAST>
+__device__ __forceinline__ void fwd_pass1(C2<float>* a, const Tw<float>& W, const float* __restrict__ rowA, const float* __restrict__ rowB,
+                                          int wb, int R, int lim, int t) {
+    constexpr int L = kF / 8, LP = L + L / 16;
+    auto load2 = [&](int n, float2& xa, float2& xb) {
+        if constexpr (FAST) {
+            xa = __ldg(reinterpret_cast<const float2*>(rowA + wb + n));
+            xb = __ldg(reinterpret_cast<const float2*>(rowB + wb + n));
+        } else {
+            xa = make_float2(0.f, 0.f);
+            xb = make_float2(0.f, 0.f);
+            if (n < lim) {  // lim and n are even: the pair is inside or outside together; n < lim <= R: one wrap at most
+                int sl = wb + n;
+                if (sl >= R) sl -= R;
+                xa = __ldg(reinterpret_cast<const float2*>(rowA + sl));
+                xb = __ldg(reinterpret_cast<const float2*>(rowB + sl));
+            }
+        }
+    };
 #pragma unroll 1
-        for (int k = 0; k < kF / 8 / kNT / 2; k++) {
-            const int j = 2 * (t + kNT * k);
-            C2<float> v0[8], v1[8], w[8];
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const int n = j + r * L;
-                float2 xa = make_float2(0.f, 0.f), xb = make_float2(0.f, 0.f);
-                if (n < lim) {  // T, w0 and n are even: the pair is inside or outside together
-                    xa = __ldg(reinterpret_cast<const float2*>(rowA + n));
-                    if (hasB) xb = __ldg(reinterpret_cast<const float2*>(rowB + n));
-                }
+    for (int k = 0; k < kF / 8 / kNT / 2; k++) {
+        const int j = 2 * (t + kNT * k);
+        C2<float> v0[8], v1[8], w[8];
+        C2<float> wj0 = {1.f, 0.f}, wj1 = {1.f, 0.f};
+        if constexpr (MODE == 2) { wj0 = W.at2(j); wj1 = W.at2(j + 1); }
+        static_for<8>([&](auto rr) {
+            constexpr int r = decltype(rr)::value;
+            const int n = j + r * L;
+            float2 xa, xb;
+            load2(n, xa, xb);
+            if constexpr (MODE == 0) {
                 v0[r] = C2<float>{xa.x, xb.x};
                 v1[r] = C2<float>{xa.y, xb.y};
+            } else {
+                float2 ya, yb;
+                load2(n + kF, ya, yb);
+                if constexpr (MODE == 1) {
+                    v0[r] = C2<float>{xa.x + ya.x, xb.x + yb.x};
+                    v1[r] = C2<float>{xa.y + ya.y, xb.y + yb.y};
+                } else {  // (z[n] - z[n+8192]) W16384^(j + 1024 r) = ... W16384^j W16^r
+                    v0[r] = tw<16, r, false, float>(cmul(C2<float>{xa.x - ya.x, xb.x - yb.x}, wj0));
+                    v1[r] = tw<16, r, false, float>(cmul(C2<float>{xa.y - ya.y, xb.y - yb.y}, wj1));
+                }
             }
-            constexpr int LP = L + L / 16;
-            C2<float>* p = a + pad(j);  // j is even: j and j + 1 share the padding offset
-            twiddles8<1>(W, j, w);
-            fft_dif<8>(v0);
-            p[0] = v0[0];
+        });
+        C2<float>* p = a + pad(j);  // j is even: j and j + 1 share the padding offset
+        twiddles8<1>(W, j, w);
+        fft_dif<8>(v0);
+        p[0] = v0[0];
 #pragma unroll
-            for (int s = 1; s < 8; s++) p[bitrev3(s) * LP] = cmul(v0[s], w[bitrev3(s)]);
-            twiddles8<1>(W, j + 1, w);
-            fft_dif<8>(v1);
-            p[1] = v1[0];
+        for (int s = 1; s < 8; s++) p[bitrev3(s) * LP] = cmul(v0[s], w[bitrev3(s)]);
+        twiddles8<1>(W, j + 1, w);
+        fft_dif<8>(v1);
+        p[1] = v1[0];
 #pragma unroll
-            for (int s = 1; s < 8; s++) p[1 + bitrev3(s) * LP] = cmul(v1[s], w[bitrev3(s)]);
-        }
+        for (int s = 1; s < 8; s++) p[1 + bitrev3(s) * LP] = cmul(v1[s], w[bitrev3(s)]);
     }
-    __syncthreads();
-    fwd_pass8<kF / 8>(a, W, t);
-    __syncthreads();
-    fwd_pass8<kF / 64>(a, W, t);
-    __syncthreads();
-    // forward pass 4 (radix 16, no twiddles) . spectrum product . inverse pass 4, all in registers
+}
+
+// forward pass 4 (radix 16, no twiddles) . spectrum product . inverse pass 4, all in registers
+__device__ __forceinline__ void mid_pass16(C2<float>* a, const C2<float>* __restrict__ H, int t) {
 #pragma unroll 1
     for (int k = 0; k < kF / 16 / kNT; k++) {
         const int u = t + kNT * k, base = 16 * u;
@@ -327,48 +372,135 @@ fir_fft_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, fl
 #pragma unroll
         for (int s = 0; s < 16; s++) a[pad(base) + s] = v[s];
     }
+}
+
+template <int MODE, bool FAST>
+__device__ __forceinline__ void inv_pass1(const C2<float>* a, const Tw<float>& W, float* __restrict__ outA, float* __restrict__ outB,
+                                          bool hasB, int hist, int lim, float divisor, float post_nf, float4* __restrict__ scr, int t) {
+    constexpr int L = kF / 8, LP = L + L / 16;
+    const bool post = post_nf != 0.0f;
+    const float post_rnf = post ? __frcp_rn(post_nf) : 0.0f;
+    auto fin = [&](float y) {
+        y = __fmul_rn(y, divisor);
+        return post ? div_nf(y, post_nf, post_rnf) : y;
+    };
+    auto store2 = [&](int n, float a0, float a1, float b0, float b1) {  // samples n, n + 1 of both channels
+        *reinterpret_cast<float2*>(outA + n) = make_float2(fin(a0), fin(a1));
+        if (hasB) *reinterpret_cast<float2*>(outB + n) = make_float2(fin(b0), fin(b1));
+    };
+#pragma unroll 1
+    for (int k = 0; k < kF / 8 / kNT / 2; k++) {
+        const int j = 2 * (t + kNT * k);
+        C2<float> v0[8], v1[8], w[8];
+        const C2<float>* p = a + pad(j);
+        twiddles8<1>(W, j, w);
+        v0[0] = p[0];
+#pragma unroll
+        for (int s = 1; s < 8; s++) v0[s] = cmulc(p[bitrev3(s) * LP], w[bitrev3(s)]);
+        ifft_dit<8>(v0);
+        twiddles8<1>(W, j + 1, w);
+        v1[0] = p[1];
+#pragma unroll
+        for (int s = 1; s < 8; s++) v1[s] = cmulc(p[1 + bitrev3(s) * LP], w[bitrev3(s)]);
+        ifft_dit<8>(v1);
+        float4* sc = scr + (k * 8) * kNT + t;  // [k][r][thread]: coalesced, and read back by the thread that wrote it
+        if constexpr (MODE == 1) {
+#pragma unroll
+            for (int r = 0; r < 8; r++) __stcg(sc + r * kNT, make_float4(v0[r].x, v0[r].y, v1[r].x, v1[r].y));
+        } else if constexpr (MODE == 2) {
+            const C2<float> wj0 = W.at2(j), wj1 = W.at2(j + 1);
+            float4 e[8];
+#pragma unroll
+            for (int r = 0; r < 8; r++) e[r] = __ldcg(sc + r * kNT);
+            static_for<8>([&](auto rr) {
+                constexpr int r = decltype(rr)::value;
+                const int n = j + r * L;
+                const C2<float> t0 = tw<16, r, true, float>(cmulc(v0[r], wj0));  // W16384^-(j + 1024 r) o'[n]
+                const C2<float> t1 = tw<16, r, true, float>(cmulc(v1[r], wj1));
+                if (FAST ? r >= 4 : n >= hist) store2(n, e[r].x + t0.x, e[r].z + t1.x, e[r].y + t0.y, e[r].w + t1.y);
+                store2(n + kF, e[r].x - t0.x, e[r].z - t1.x, e[r].y - t0.y, e[r].w - t1.y);
+            });
+        } else {
+            static_for<8>([&](auto rr) {
+                constexpr int r = decltype(rr)::value;
+                const int n = j + r * L;
+                if (FAST ? r >= 4 : (n >= hist && n < lim)) store2(n, v0[r].x, v1[r].x, v0[r].y, v1[r].y);
+            });
+        }
+    }
+}
+
+template <int MODE, bool FAST>
+__device__ __forceinline__ void transform(C2<float>* a, const Tw<float>& W, const FftArgs& g, const float* rowA, const float* rowB,
+                                          float* outA, float* outB, bool hasB, int wb, int lim, float4* scr, int t) {
+    fwd_pass1<MODE, FAST>(a, W, rowA, rowB, wb, g.u_ring, lim, t);
+    __syncthreads();
+    fwd_pass8<kF / 8>(a, W, t);
+    __syncthreads();
+    fwd_pass8<kF / 64>(a, W, t);
+    __syncthreads();
+    mid_pass16(a, reinterpret_cast<const C2<float>*>(MODE == 0 ? g.H13 : MODE == 1 ? g.H14e : g.H14o), t);
     __syncthreads();
     inv_pass8<kF / 64>(a, W, t);
     __syncthreads();
     inv_pass8<kF / 8>(a, W, t);
     __syncthreads();
-    // inverse pass 1: results straight to global memory (only the V valid samples), two samples per store
-    {
-        constexpr int L = kF / 8;
-        float* outA = Y + (long long)chA * y_stride + s0 - (Ne - 1);
-        float* outB = Y + (long long)chB * y_stride + s0 - (Ne - 1);
-        const bool post = post_nf != 0.0f;
-        const float post_rnf = post ? __frcp_rn(post_nf) : 0.0f;
-#pragma unroll 1
-        for (int k = 0; k < kF / 8 / kNT / 2; k++) {
-            const int j = 2 * (t + kNT * k);
-            C2<float> v0[8], v1[8], w[8];
-            constexpr int LP = L + L / 16;
-            const C2<float>* p = a + pad(j);
-            twiddles8<1>(W, j, w);
-            v0[0] = p[0];
-#pragma unroll
-            for (int s = 1; s < 8; s++) v0[s] = cmulc(p[bitrev3(s) * LP], w[bitrev3(s)]);
-            ifft_dit<8>(v0);
-            twiddles8<1>(W, j + 1, w);
-            v1[0] = p[1];
-#pragma unroll
-            for (int s = 1; s < 8; s++) v1[s] = cmulc(p[1 + bitrev3(s) * LP], w[bitrev3(s)]);
-            ifft_dit<8>(v1);
-#pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const int n = j + r * L;
-                if (n >= Ne - 1 && n < lim) {
-                    float2 ya = make_float2(__fmul_rn(v0[r].x, divisor), __fmul_rn(v1[r].x, divisor));
-                    float2 yb = make_float2(__fmul_rn(v0[r].y, divisor), __fmul_rn(v1[r].y, divisor));
-                    if (post) {
-                        ya.x = div_nf(ya.x, post_nf, post_rnf); ya.y = div_nf(ya.y, post_nf, post_rnf);
-                        yb.x = div_nf(yb.x, post_nf, post_rnf); yb.y = div_nf(yb.y, post_nf, post_rnf);
-                    }
-                    *reinterpret_cast<float2*>(outA + n) = ya;
-                    if (hasB) *reinterpret_cast<float2*>(outB + n) = yb;
-                }
+    inv_pass1<MODE, FAST>(a, W, outA, outB, hasB, g.hist, lim, g.divisor, g.post_nf, scr, t);
+}
+
+__global__ void __launch_bounds__(kNT, 3)
+fir_fft_kernel(const __grid_constant__ FftArgs g) {
+    extern __shared__ float2 smem_f2[];
+    __shared__ int s_item;
+    C2<float>* a = reinterpret_cast<C2<float>*>(smem_f2);
+    const int t = threadIdx.x;
+    const Tw<float> W = load_tables<float>(a + kPadded, g.Wg, t);
+    float4* scr = g.scratch + (size_t)blockIdx.x * (kF / 2);
+    const int q = g.n14 + g.n13;
+    const int V13 = kF - g.hist, V14 = 2 * kF - g.hist;
+    for (;;) {
+        __syncthreads();  // the previous item's last pass has read the shared array (and s_item); tables visible
+        if (t == 0) s_item = (int)atomicAdd(g.work, 1u);
+        __syncthreads();
+        const int item = s_item;
+        if (item >= g.n_items) break;
+        const int pr = item / q, sg = item - pr * q;
+        const int chA = g.c_begin + 2 * pr, chB = chA + 1;
+        const bool hasB = chB < g.c_end;
+        const bool dbl = sg < g.n14;
+        const long long s0 = dbl ? (long long)sg * V14 : (long long)g.n14 * V14 + (long long)(sg - g.n14) * V13;
+        const long long w0 = s0 - g.hist;                      // call-relative index of window sample 0 (>= -hist)
+        const int win = dbl ? 2 * kF : kF;
+        const long long lim_ll = g.T - w0;                     // window samples >= lim lie beyond this call's input: zeros
+        const int lim = lim_ll > win ? win : (int)lim_ll;
+        const int wb = ring_slot(g.u_pos, (int)w0, g.u_ring);  // ring slot of window sample 0
+        const float* rowA = g.U + (long long)chA * g.u_stride;
+        const float* rowB = g.U + (long long)(hasB ? chB : chA) * g.u_stride;  // odd channel count: B mirrors A, never stored
+        float* outA = g.Y + (long long)chA * g.y_stride + w0;
+        float* outB = g.Y + (long long)(hasB ? chB : chA) * g.y_stride + w0;
+        const bool fast = g.hist == kF / 2 && lim == win && wb + win <= g.u_ring;
+        if (dbl) {  // lim == win is guaranteed by the launcher (double segments lie fully inside the call)
+            if (fast) {
+                transform<1, true>(a, W, g, rowA, rowB, outA, outB, hasB, wb, lim, scr, t);
+                __syncthreads();
+                transform<2, true>(a, W, g, rowA, rowB, outA, outB, hasB, wb, lim, scr, t);
+            } else {
+                transform<1, false>(a, W, g, rowA, rowB, outA, outB, hasB, wb, lim, scr, t);
+                __syncthreads();
+                transform<2, false>(a, W, g, rowA, rowB, outA, outB, hasB, wb, lim, scr, t);
             }
+        } else if (fast) {
+            transform<0, true>(a, W, g, rowA, rowB, outA, outB, hasB, wb, lim, scr, t);
+        } else {
+            transform<0, false>(a, W, g, rowA, rowB, outA, outB, hasB, wb, lim, scr, t);
+        }
+    }
+    // the last CTA out re-arms the work counter for the next launch on this lane (stream-ordered behind this one)
+    if (t == 0) {
+        __threadfence();
+        if (atomicAdd(g.work + 1, 1u) == gridDim.x - 1) {
+            g.work[0] = 0;
+            g.work[1] = 0;
         }
     }
 }
@@ -391,6 +523,7 @@ fir_fft_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, fl
 // padding), + the twiddle tables stored duplicated (wr, wr, wi, wi) so one LDS.128 yields packed operands.
 typedef unsigned long long u64;
 constexpr int kH2 = kF / 2;  // points of each sub-transform
+constexpr int kFineP = 16;   // fine twiddle entries of this kernel (W8192^b, b < 16)
 struct VF { u64 re, im; };   // packed complex pair: lo half = E, hi half = O
 struct WF { u64 re, im; };   // one twiddle, duplicated into both halves
 __device__ __forceinline__ u64 pk(float lo, float hi) { return (u64)__float_as_uint(lo) | ((u64)__float_as_uint(hi) << 32); }
@@ -535,25 +668,29 @@ __device__ __forceinline__ void inv_pass8v(float4* a, const TwP& W, int t) {
 // Window of segment s: call-relative samples [4096 (s - 1), 4096 (s + 1)); outputs [4096 s, 4096 (s + 1)).
 // Requires n_taps <= 4097 (taps beyond the stored history multiply zeros: samples before -hist_pad read as 0).
 __global__ void __launch_bounds__(kNT, 3)
-fir_fft_packed_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, float* __restrict__ Y, long long y_stride,
+fir_fft_packed_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, int u_ring, int u_pos, float* __restrict__ Y, long long y_stride,
                       const float4* __restrict__ Hg, const float2* __restrict__ Wg, long long T, float divisor, float post_nf,
                       int c_begin, int c_end) {
     extern __shared__ float4 smem_f4[];
     float4* a = smem_f4;  // [4096]
     float4* tab = a + kH2;
     const int t = threadIdx.x;
-    for (int i = t; i < kCoarse; i += kNT) { const float2 w = Wg[16 * i]; tab[i] = make_float4(w.x, w.x, w.y, w.y); }
-    if (t < kFine) { const float2 w = Wg[t]; tab[kCoarse + t] = make_float4(w.x, w.x, w.y, w.y); }
+    for (int i = t; i < kCoarse; i += kNT) { const float2 w = Wg[i]; tab[i] = make_float4(w.x, w.x, w.y, w.y); }
+    if (t < kFineP) { const float2 w = Wg[kCoarse + 2 * t]; tab[kCoarse + t] = make_float4(w.x, w.x, w.y, w.y); }  // W8192^t = fine[2 t]
     const TwP W{tab, tab + kCoarse};
     const long long s0 = (long long)blockIdx.x * kH2;
     const int chA = c_begin + 2 * blockIdx.y, chB = chA + 1;
     const bool hasB = chB < c_end;
-    const float* rowA = U + (long long)chA * u_stride + hist_pad + (s0 - kH2);
-    const float* rowB = U + (long long)(hasB ? chB : chA) * u_stride + hist_pad + (s0 - kH2);
+    const float* rowA = U + (long long)chA * u_stride;  // ring rows: window sample i at slot (wb + i) mod u_ring
+    const float* rowB = U + (long long)(hasB ? chB : chA) * u_stride;
     // window samples below lo precede the stored history, samples >= lim lie beyond this call's input: zeros.
     // 0 <= lo <= 4096 < lim <= 8192 after clamping, so [lo, lim) is never empty and clamped indices are loadable.
     const long long lo_ll = -(long long)hist_pad - (s0 - kH2), lim_ll = T - (s0 - kH2);
     const int lo = lo_ll < 0 ? 0 : (int)lo_ll, lim = lim_ll > kF ? kF : (int)lim_ll;
+    // ring slot of window sample `lo` (the first loadable one: lo - kH2 + s0 >= -hist_pad); loaded samples i lie in
+    // [lo, lim), lim - lo <= hist_pad + T <= u_ring: one wrap at most
+    const int wlo = ring_slot(u_pos, (int)(s0 - kH2 + lo), u_ring);
+    auto slot = [&](int i) { int p = wlo + (i - lo); return p >= u_ring ? p - u_ring : p; };
     __syncthreads();
 
     // ---- forward pass 0: global -> radix-2 split -> radix-8 (M = 4096) -> shared
@@ -568,7 +705,8 @@ fir_fft_packed_kernel(const float* __restrict__ U, long long u_stride, int hist_
             // branch-free (clamped index, select afterwards) so that all 32 loads of a butterfly are issued back to back
             const int i0 = min(max(n, lo), lim - 1), i1 = min(n + kH2, lim - 1);  // n + 4096 >= lo always
             const bool ok0 = n >= lo && n < lim, ok1 = n + kH2 < lim;
-            float a0 = __ldg(rowA + i0), b0 = __ldg(rowB + i0), a1 = __ldg(rowA + i1), b1 = __ldg(rowB + i1);
+            const int p0 = slot(i0), p1 = slot(i1);
+            float a0 = __ldg(rowA + p0), b0 = __ldg(rowB + p0), a1 = __ldg(rowA + p1), b1 = __ldg(rowB + p1);
             a0 = ok0 ? a0 : 0.f; b0 = (ok0 && hasB) ? b0 : 0.f; a1 = ok1 ? a1 : 0.f; b1 = (ok1 && hasB) ? b1 : 0.f;
             const C2<float> d = tw<16, r, false, float>(cmul(C2<float>{a0 - a1, b0 - b1}, wj));  // (z[n] - z[n+4096]) W_F^(j + 512 r)
             v[r] = VF{pk(a0 + a1, d.x), pk(b0 + b1, d.y)};
@@ -670,14 +808,21 @@ __global__ void fir_spectrum_packed_kernel(const double* __restrict__ taps_rev, 
     Hout[idx] = make_float4((float)acc[0], (float)acc[1], (float)acc[2], (float)acc[3]);
 }
 
-// ---- spectrum of h in the transform's own output order (f64), scaled by 1/F -----------------------------
+// ---- spectrum of h in the transform's own output order (f64) -----------------------------------------------
+// odd = 0: FFT8192(h) * scale (the bins of an 8192-point segment; with scale 1/16384 the EVEN bins of a 16384-point one,
+// because h[n + 8192] = 0).  odd = 1: FFT8192(h[n] W16384^n) * scale = the ODD bins of the 16384-point spectrum.
 __global__ void __launch_bounds__(kNT, 1)
-fir_spectrum_kernel(const double* __restrict__ taps_rev, int N, const double2* __restrict__ Wd, float2* __restrict__ Hout) {
+fir_spectrum_kernel(const double* __restrict__ taps_rev, int N, const double2* __restrict__ Wd, float2* __restrict__ Hout, int odd, double scale) {
     extern __shared__ double2 smem_d2[];
     C2<double>* a = reinterpret_cast<C2<double>*>(smem_d2);
     const int t = threadIdx.x;
     const Tw<double> W = load_tables<double>(a + kPadded, Wd, t);
-    for (int n = t; n < kF; n += kNT) a[pad(n)] = C2<double>{n < N ? taps_rev[N - 1 - n] : 0.0, 0.0};  // h[n] = taps[N-1-n]
+    for (int n = t; n < kF; n += kNT) {
+        const double h = n < N ? taps_rev[N - 1 - n] : 0.0;  // h[n] = taps[N-1-n]
+        double sn = 0.0, cs = 1.0;
+        if (odd) sincospi(-(double)n / (double)kF, &sn, &cs);  // W16384^n, exact argument
+        a[pad(n)] = C2<double>{h * cs, h * sn};
+    }
     __syncthreads();
     fwd_pass8<kF>(a, W, t);
     __syncthreads();
@@ -692,52 +837,85 @@ fir_spectrum_kernel(const double* __restrict__ taps_rev, int N, const double2* _
         for (int s = 0; s < 16; s++) v[s] = a[pad(base) + s];
         fft_dif<16>(v);
 #pragma unroll
-        for (int s = 0; s < 16; s++)  // [k][s / 2][thread] float4 order, see fir_fft_kernel
-            Hout[((k * 8 + (s >> 1)) * kNT + t) * 2 + (s & 1)] = make_float2((float)(v[s].x / kF), (float)(v[s].y / kF));
+        for (int s = 0; s < 16; s++)  // [k][s / 2][thread] float4 order, see mid_pass16
+            Hout[((k * 8 + (s >> 1)) * kNT + t) * 2 + (s & 1)] = make_float2((float)(v[s].x * scale), (float)(v[s].y * scale));
     }
 }
 
 struct Tables {
-    float2* Wf = nullptr;
+    float2* Wf = nullptr;    // compact twiddle table [512 coarse + 32 fine] (see Tw)
     double2* Wd = nullptr;
+    int n_sm = 0;
 };
-Tables g_tab_dev[kMaxDevices];  // twiddle tables live in one device's memory: one set per device, built once
+Tables g_tab_dev[kMaxDevices];  // device memory: one set per device, built once
 std::mutex g_tab_mu;
 #define g_tab g_tab_dev[current_device_slot()]
 
 int ensure_tables() {
     std::lock_guard<std::mutex> lk(g_tab_mu);
     if (g_tab.Wf) return 0;
-    std::vector<float2> wf(kF);
-    std::vector<double2> wd(kF);
-    for (int k = 0; k < kF; k++) {
-        const double ang = -2.0 * M_PI * (double)k / (double)kF;
+    constexpr int n = kCoarse + kFine;
+    std::vector<float2> wf(n);
+    std::vector<double2> wd(n);
+    for (int k = 0; k < n; k++) {
+        const double ang = k < kCoarse ? -2.0 * M_PI * (double)k / (double)kCoarse : -2.0 * M_PI * (double)(k - kCoarse) / (2.0 * kF);
         wd[k] = make_double2(std::cos(ang), std::sin(ang));
         wf[k] = make_float2((float)wd[k].x, (float)wd[k].y);
     }
     cudaError_t e;
-    if ((e = cudaMalloc(&g_tab.Wf, kF * sizeof(float2))) != cudaSuccess) return (int)e;
-    if ((e = cudaMalloc(&g_tab.Wd, kF * sizeof(double2))) != cudaSuccess) return (int)e;
-    if ((e = cudaMemcpy(g_tab.Wf, wf.data(), kF * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
-    if ((e = cudaMemcpy(g_tab.Wd, wd.data(), kF * sizeof(double2), cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
+    float2* f = nullptr;
+    double2* d = nullptr;
+    if ((e = cudaMalloc(&f, n * sizeof(float2))) != cudaSuccess) return (int)e;
+    if ((e = cudaMalloc(&d, n * sizeof(double2))) != cudaSuccess) return (int)e;
+    if ((e = cudaMemcpy(f, wf.data(), n * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
+    if ((e = cudaMemcpy(d, wd.data(), n * sizeof(double2), cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
+    int dev = 0, n_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    g_tab.n_sm = n_sm > 0 ? n_sm : 148;
+    g_tab.Wd = d;
+    g_tab.Wf = f;
     return 0;
 }
+
+constexpr int kMaxCtas = 3 * 192;  // persistent grid: 3 CTAs per SM, scratch slots sized for up to 192 SMs
+constexpr size_t kWorkHeader = 256;
 
 }  // namespace
 
 int fir_fft_max_taps() { return kF / 2 + 1; }
+size_t fir_fft_spectrum_bytes() { return (size_t)4 * kF * sizeof(float2); }  // H13 | packed-kernel order | H14 even | H14 odd
+size_t fir_fft_work_bytes() { return kWorkHeader + (size_t)kMaxCtas * (kF / 2) * sizeof(float4); }
 static int effective_taps(int n) { return (n - 1 + 3) / 4 * 4 + 1; }  // Ne - 1 multiple of 4
+
+// Segment plan of one call: n14 double (16384-point) segments first, then n13 single ones.  A double segment costs
+// about kCost14 single ones (two sub-transforms + the radix-2 step and the scratch round trip) and must lie fully
+// inside the call.  DSPB_FIR_F14=0 disables double segments (the round-1 behaviour).
+static void segment_plan(int hist, int64_t T, int* n14, int* n13) {
+    static const int f14_env = getenv("DSPB_FIR_F14") ? atoi(getenv("DSPB_FIR_F14")) : -1;
+    constexpr double kCost14 = 2.3;
+    const int64_t V13 = kF - hist, V14 = 2 * kF - hist;
+    bool use14 = kCost14 / (double)V14 < 1.0 / (double)V13;
+    if (f14_env == 0) use14 = false;
+    if (f14_env == 1) use14 = true;
+    int64_t a = use14 ? T / V14 : 0;
+    // the rest: single segments, unless one more double segment would be cheaper -- it would not fit, so no
+    const int64_t rem = T - a * V14;
+    *n14 = (int)a;
+    *n13 = (int)((rem + V13 - 1) / V13);
+}
 
 int launch_fir_fft(const FirPlan& fp, const float* U, int64_t u_stride, float* Y, int64_t y_stride, int c_begin, int c_end,
                    int64_t T, int64_t started, cudaStream_t st, int* n_launches) {
     (void)started;
     if (fp.log2F != kLog2F || fp.n_taps > fir_fft_max_taps() || fp.n_taps < 1) return (int)cudaErrorInvalidValue;
+    if (fp.u_ring <= 0 || (fp.u_ring & 127) || fp.hist_pad + T > fp.u_ring) return (int)cudaErrorInvalidValue;
     int rc = ensure_tables();
     if (rc) return rc;
     if (fp.mode == FIR_FFT_PACKED) {  // opt-in: measured 5 % slower than the scalar kernel (see the comment above VF)
         static std::atomic<bool> configured2_dev[kMaxDevices];
         std::atomic<bool>& configured2 = configured2_dev[current_device_slot()];
-        const int smem2 = (kH2 + kCoarse + kFine) * (int)sizeof(float4);
+        const int smem2 = (kH2 + kCoarse + kFineP) * (int)sizeof(float4);
         if (!configured2.load(std::memory_order_acquire)) {
             cudaError_t e = cudaFuncSetAttribute(fir_fft_packed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2);
             if (e != cudaSuccess) return (int)e;
@@ -745,15 +923,16 @@ int launch_fir_fft(const FirPlan& fp, const float* U, int64_t u_stride, float* Y
         }
         const long long n_seg2 = (T + kH2 - 1) / kH2;
         const int pairs2 = (c_end - c_begin + 1) / 2;
-        const float4* Hp = reinterpret_cast<const float4*>(fp.H + kF);  // packed-order spectrum follows the v1 table
+        const float4* Hp = reinterpret_cast<const float4*>(fp.H + kF);  // packed-order spectrum follows the H13 table
         for (int p0 = 0; p0 < pairs2; p0 += 65535) {
             dim3 grid((unsigned)n_seg2, (unsigned)std::min(65535, pairs2 - p0));
-            fir_fft_packed_kernel<<<grid, kNT, smem2, st>>>(U, u_stride, fp.hist_pad, Y, y_stride, Hp, g_tab.Wf, T, fp.divisor, fp.post_nf,
-                                                           c_begin + 2 * p0, c_end);
+            fir_fft_packed_kernel<<<grid, kNT, smem2, st>>>(U, u_stride, fp.hist_pad, fp.u_ring, fp.u_pos, Y, y_stride, Hp, g_tab.Wf, T, fp.divisor,
+                                                           fp.post_nf, c_begin + 2 * p0, c_end);
             if (n_launches) *n_launches += 1;
         }
         return (int)cudaGetLastError();
     }
+    if (!fp.fft_work) return (int)cudaErrorInvalidValue;
     static std::atomic<bool> configured_dev[kMaxDevices];
     std::atomic<bool>& configured = configured_dev[current_device_slot()];
     const int smem = (kPadded + kCoarse + kFine) * (int)sizeof(float2);
@@ -762,16 +941,33 @@ int launch_fir_fft(const FirPlan& fp, const float* U, int64_t u_stride, float* Y
         if (e != cudaSuccess) return (int)e;
         configured.store(true, std::memory_order_release);
     }
-    const int Ne = effective_taps(fp.n_taps);
-    const int V = kF - Ne + 1;
-    const long long n_seg = (T + V - 1) / V;
-    const int pairs = (c_end - c_begin + 1) / 2;
-    for (int p0 = 0; p0 < pairs; p0 += 65535) {
-        dim3 grid((unsigned)n_seg, (unsigned)std::min(65535, pairs - p0));
-        fir_fft_kernel<<<grid, kNT, smem, st>>>(U, u_stride, fp.hist_pad, Y, y_stride, fp.H, g_tab.Wf, Ne, T, fp.divisor, fp.post_nf,
-                                               c_begin + 2 * p0, c_end);
-        if (n_launches) *n_launches += 1;
-    }
+    FftArgs g;
+    g.U = U;
+    g.u_stride = u_stride;
+    g.u_ring = fp.u_ring;
+    g.u_pos = fp.u_pos;
+    g.hist = effective_taps(fp.n_taps) - 1;
+    g.Y = Y;
+    g.y_stride = y_stride;
+    g.H13 = fp.H;
+    g.H14e = fp.H + 2 * kF;
+    g.H14o = fp.H + 3 * kF;
+    g.Wg = g_tab.Wf;
+    g.T = T;
+    g.divisor = fp.divisor;
+    g.post_nf = fp.post_nf;
+    g.c_begin = c_begin;
+    g.c_end = c_end;
+    segment_plan(g.hist, T, &g.n14, &g.n13);
+    const long long pairs = (c_end - c_begin + 1) / 2;
+    const long long n_items = pairs * (g.n14 + g.n13);
+    if (n_items <= 0 || n_items > (1ll << 30)) return (int)cudaErrorInvalidValue;
+    g.n_items = (int)n_items;
+    g.work = reinterpret_cast<unsigned*>(fp.fft_work);
+    g.scratch = reinterpret_cast<float4*>(reinterpret_cast<char*>(fp.fft_work) + kWorkHeader);
+    const int grid = (int)std::min<long long>(n_items, std::min(kMaxCtas, 3 * g_tab.n_sm));
+    fir_fft_kernel<<<grid, kNT, smem, st>>>(g);
+    if (n_launches) *n_launches += 1;
     return (int)cudaGetLastError();
 }
 
@@ -782,8 +978,11 @@ int fir_prepare_spectrum(int log2F, const double* taps_rev_dev, int n_taps, floa
     const int smem = (kPadded + kCoarse + kFine) * (int)sizeof(double2);
     cudaError_t e = cudaFuncSetAttribute(fir_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
-    fir_spectrum_kernel<<<1, kNT, smem, (cudaStream_t)stream>>>(taps_rev_dev, n_taps, g_tab.Wd, H_dev);
-    fir_spectrum_packed_kernel<<<kH2 / 128, 128, 0, (cudaStream_t)stream>>>(taps_rev_dev, n_taps, reinterpret_cast<float4*>(H_dev + kF));
+    cudaStream_t st = (cudaStream_t)stream;
+    fir_spectrum_kernel<<<1, kNT, smem, st>>>(taps_rev_dev, n_taps, g_tab.Wd, H_dev, 0, 1.0 / kF);
+    fir_spectrum_packed_kernel<<<kH2 / 128, 128, 0, st>>>(taps_rev_dev, n_taps, reinterpret_cast<float4*>(H_dev + kF));
+    fir_spectrum_kernel<<<1, kNT, smem, st>>>(taps_rev_dev, n_taps, g_tab.Wd, H_dev + 2 * kF, 0, 0.5 / kF);
+    fir_spectrum_kernel<<<1, kNT, smem, st>>>(taps_rev_dev, n_taps, g_tab.Wd, H_dev + 3 * kF, 1, 0.5 / kF);
     return (int)cudaGetLastError();
 }
 

@@ -140,7 +140,7 @@ __global__ void toeplitz_tiles_kernel(const double* __restrict__ taps_rev, int N
 // 16-byte core-matrix rows.  Only rows of channels in [c_begin, c_end) are written (other chunks of the engine
 // own the rest; an output column only ever depends on its own row).
 __global__ void __launch_bounds__(256)
-x_split_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, long long T, int Hb, int n_sb, uint8_t* __restrict__ Xt,
+x_split_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, int u_ring, int u_pos, long long T, int Hb, int n_sb, uint8_t* __restrict__ Xt,
                int c_begin, int c_end, int cb0) {
     const int sb = blockIdx.x, cb = cb0 + blockIdx.y;
     const int row = threadIdx.x;
@@ -148,18 +148,19 @@ x_split_kernel(const float* __restrict__ U, long long u_stride, int hist_pad, lo
     if (ch < c_begin || ch >= c_end) return;
     uint8_t* tile = Xt + ((size_t)cb * n_sb + sb) * 2 * kBBytes;
     const long long s0 = (long long)sb * kBK - Hb;
-    const float* src = U + (long long)ch * u_stride + hist_pad;
+    const float* src = U + (long long)ch * u_stride;  // ring row: call sample s at slot (u_pos + s) mod u_ring (plan.h)
 #pragma unroll
     for (int kc = 0; kc < kBK / 8; kc++) {
         const long long s = s0 + kc * 8;
         float x[8];
         if (s >= -(long long)hist_pad && s + 8 <= T) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(src + s));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(src + s + 4));
+            const int sl = ring_slot(u_pos, (int)s, u_ring);  // s is a multiple of 8: the chunk does not wrap
+            const float4 a = __ldg(reinterpret_cast<const float4*>(src + sl));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(src + sl + 4));
             x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
         } else {
 #pragma unroll
-            for (int e = 0; e < 8; e++) x[e] = (s + e >= -(long long)hist_pad && s + e < T) ? src[s + e] : 0.0f;
+            for (int e = 0; e < 8; e++) x[e] = (s + e >= -(long long)hist_pad && s + e < T) ? src[ring_slot(u_pos, (int)(s + e), u_ring)] : 0.0f;
         }
         uint32_t hi[4], lo[4];
 #pragma unroll
@@ -315,7 +316,7 @@ int launch_fir_toeplitz(const FirPlan& fp, const float* U, int64_t u_stride, flo
     uint8_t* Xt = reinterpret_cast<uint8_t*>(fp.toep_split);
     for (int c = cb0; c < cb1; c += 32768) {
         const int nb = cb1 - c < 32768 ? cb1 - c : 32768;
-        x_split_kernel<<<dim3((unsigned)n_sb, (unsigned)nb), 256, 0, st>>>(U, u_stride, fp.hist_pad, T, dmax, n_sb_alloc, Xt, c_begin, c_end, c);
+        x_split_kernel<<<dim3((unsigned)n_sb, (unsigned)nb), 256, 0, st>>>(U, u_stride, fp.hist_pad, fp.u_ring, fp.u_pos, T, dmax, n_sb_alloc, Xt, c_begin, c_end, c);
         fir_toeplitz_kernel<<<dim3((unsigned)n_tiles, (unsigned)nb), kThreadsT, kSmemBytes, st>>>(
             reinterpret_cast<const uint8_t*>(fp.toep_tiles), Xt, Y, y_stride, nK, n_sb_alloc, T, fp.divisor, fp.post_nf, c_begin, c_end, c);
         if (n_launches) *n_launches += 2;

@@ -248,13 +248,20 @@ struct Ctx {
     float* out_row;
     float* ring_row;
     int ring_D;
+    int out_ring, out_pos;  // the first stored output is a ring-addressed FIR input (BufDesc::ring_len / ring_pos), or 0
     mutable int ring_slot;  // this thread's ring slot of the tile whose comb runs next
 
     template <class P>
     __device__ __forceinline__ void init_streams(const P& pr) {
         in_row = nullptr; out_row = nullptr; ring_row = nullptr; ring_D = 1; ring_slot = 0;
         if (pr.pf_buf[0] >= 0) { const BufDesc& b = pr.bufs[pr.pf_buf[0]]; in_row = b.base + (long long)ch * b.row_stride; }
-        if (pr.st_buf >= 0) { const BufDesc& b = pr.bufs[pr.st_buf]; out_row = b.base + (long long)ch * b.row_stride; }
+        out_ring = 0; out_pos = 0;
+        if (pr.st_buf >= 0) {
+            const BufDesc& b = pr.bufs[pr.st_buf];
+            out_row = b.base + (long long)ch * b.row_stride;
+            out_ring = b.ring_len;
+            out_pos = b.ring_pos;
+        }
         if (pr.pf_ring[1] >= 0) {
             const RingDesc& r = pr.rings[pr.pf_ring[1]];
             ring_row = r.base + (long long)ch * r.D;
@@ -361,10 +368,20 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
             if (c.active) {
                 float4* p;
                 if (pfc < 0 ? op.aux != 0 : pfc != 0) {
-                    p = reinterpret_cast<float4*>(c.out_row + c.n0);
+                    int m = c.n0;
+                    if (c.out_ring) {  // FIR input ring (plan.h BufDesc): slot (ring_pos + m) mod ring_len, chunks never wrap
+                        m += c.out_pos;
+                        if (m >= c.out_ring) m -= c.out_ring;
+                    }
+                    p = reinterpret_cast<float4*>(c.out_row + m);
                 } else {
                     const BufDesc& b = prog.bufs[op.buf];
-                    p = reinterpret_cast<float4*>(b.base + (long long)c.ch * b.row_stride + c.n0);
+                    int m = c.n0;
+                    if (b.ring_len) {
+                        m += b.ring_pos;
+                        if (m >= b.ring_len) m -= b.ring_len;
+                    }
+                    p = reinterpret_cast<float4*>(b.base + (long long)c.ch * b.row_stride + m);
                 }
 #pragma unroll
                 for (int k = 0; k < kF4; k++) stg_stream(p + k, make_float4(acc[4 * k], acc[4 * k + 1], acc[4 * k + 2], acc[4 * k + 3]));

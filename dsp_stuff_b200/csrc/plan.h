@@ -14,6 +14,14 @@
 
 namespace dspb {
 
+// slot of sample (pos + i) in a ring of R samples; pos in [0, R), i in [-R, R)
+__host__ __device__ inline int ring_slot(int pos, int i, int R) {
+    int p = pos + i;
+    if (p < 0) p += R;
+    if (p >= R) p -= R;
+    return p;
+}
+
 // Launch-time caches (cudaFuncSetAttribute opt-ins, SM counts, register counts, twiddle tables) are PER DEVICE:
 // one process may hold engines on several GPUs (include/dspb200.h), and a function attribute set on device 0 says
 // nothing about device 1.  Every such cache is an array indexed by the current device ordinal.
@@ -85,8 +93,13 @@ inline constexpr bool op_reads_vreg_field(int code) {
 }
 
 struct BufDesc {       // a [C x n] f32 array in global memory
-    float* base;       // element (channel 0, sample 0 of this call)
+    float* base;       // element (channel 0, sample 0 of this call); ring_len != 0: element (channel 0, ring slot 0)
     int64_t row_stride;
+    // ring_len != 0: every row is a ring of ring_len samples (a multiple of 128) and this call's sample m lives at
+    // slot (ring_pos + m) mod ring_len.  Used for the FIR input U, so that a call's last N-1 samples are the next
+    // call's history without any copy.  ring_pos is a multiple of 128: an aligned 8-sample chunk never wraps.
+    int32_t ring_len;
+    int32_t ring_pos;
 };
 
 struct RingDesc {      // Reverb ring, [C x D] f32
@@ -126,7 +139,10 @@ struct FirPlan {
                           // FIR_FFT_PACKED: the FFT path with two sub-transforms per f32x2 register pair (experiment)
     int log2F;            // FFT size F = 1 << log2F complex points, two channels per transform
     int n_taps;           // N
-    int hist_pad;         // leading samples kept in U before this call's sample 0 (>= N-1, multiple of 4)
+    int hist_pad;         // history samples kept in U before this call's sample 0 (>= N-1, multiple of 4)
+    int u_ring;           // U rows are rings of u_ring samples (multiple of 128, >= hist_pad + T): sample i of this call
+    int u_pos;            // (i in [-hist_pad, T)) lives at slot (u_pos + i) mod u_ring
+    void* fft_work;       // FIR_FFT: per-launch-lane work area of the persistent kernel (fir_fft_work_bytes())
     const float2* H;      // [2F] spectrum of h pre-scaled by 1/F: [0, F) in the scalar kernel's output order, then F/2 float4
                           // (even bin, odd bin) pairs in the packed kernel's order
     const double* taps;   // [N] reversed taps (f64) for the warm-up path
@@ -138,12 +154,15 @@ struct FirPlan {
     void* toep_split = nullptr;
     int64_t toep_max_samples = 0;
 };
-// U: [C x (hist_pad + T)] input incl. history; Y: [C x T] output.  started = samples seen before this call.
+// U: [C x u_ring] input rings (see FirPlan::u_ring / u_pos), u_stride = row pitch; Y: [C x T] output.
+// started = samples seen before this call.
 int launch_fir(const FirPlan& fp, const float* U, int64_t u_stride, float* Y, int64_t y_stride, int c_begin, int c_end,
                int64_t T, int64_t started, void* stream, int* n_launches);
 // Computes H from the (device-resident, reversed, f64) taps with the kernel's own forward passes in f64.
 int fir_prepare_spectrum(int log2F, const double* taps_rev_dev, int n_taps, float2* H_dev, void* stream);
 int fir_fft_max_taps();
+size_t fir_fft_spectrum_bytes();   // H buffer of one tap set (all spectrum tables of the FFT kernels)
+size_t fir_fft_work_bytes();       // one launch lane's work area (work counter + per-CTA scratch)
 // device-boundary format steps (boundary.cu): stereo fold a + b, mono -> stereo duplicate; flat [C * n] streams
 int launch_fold_stereo(const float* interleaved, float* mono, long long total_mono, cudaStream_t st);
 int launch_dup_stereo(const float* mono, float* interleaved, long long total_mono, cudaStream_t st);

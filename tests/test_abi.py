@@ -74,7 +74,7 @@ def test_planning_mode_describes_every_fir_kernel_and_extension_node(lib):
     from dsp_stuff_b200 import signals as S
     from dsp_stuff_b200.engine import Engine, EngineError
 
-    want = {0: "overlap-save FFT 2^13,", 1: "direct f64 sum", 2: "Toeplitz-tiled tcgen05 GEMM", 3: "packed f32x2 variant"}
+    want = {0: "overlap-save FFT 2^13 (+ 2^14 double segments", 1: "direct f64 sum", 2: "Toeplitz-tiled tcgen05 GEMM", 3: "packed f32x2 variant"}
     for mode, text in want.items():
         e = Engine(4096, block=1024, max_samples=16384, device=-1, fir_mode=mode)
         S.target_chain(4096).apply(e)
