@@ -157,11 +157,15 @@ __device__ __forceinline__ int pad(int p) { return p + (p >> 4); }
 // Twiddle source.  W16384^n = coarse[n >> 5] * fine[n & 31] with coarse[m] = exp(-2 pi i m / 512) (512 entries) and
 // fine[b] = exp(-2 pi i b / 16384) (32 entries): 4.3 KB of shared memory instead of an L2-resident table.  The
 // 8192-point passes index in units of W8192 = W16384^2: W8192^k = coarse[k >> 4] * fine[2 (k & 15)].
-constexpr int kCoarse = kF / 16, kFine = 32;
+constexpr int kCoarse = kF / 16, kFine = 32, kT128 = 7 * 16;
+constexpr int kTwEntries = kCoarse + kFine + kT128;
 template <typename T>
 struct Tw {
     const C2<T>* coarse;  // [512] exp(-2 pi i m / 512)
     const C2<T>* fine;    // [32]  exp(-2 pi i b / 16384)
+    const C2<T>* t128;    // [7][16] W128^(j q), q = 1..7 major: the twiddles of the M = 128 pass, one conflict-free LDS.64
+                          // per value (picked out of `coarse` their 16 addresses are 32 / 64 / 128 bytes apart: up to
+                          // 16-way bank conflicts, 42 % excess wavefronts on that pass -- ncu, profiles/r02_*)
     __device__ __forceinline__ C2<T> at(int k) const {   // W8192^k
         k &= kF - 1;
         const C2<T> c = coarse[k >> 4];
@@ -201,7 +205,12 @@ template <typename T, typename TG>
 __device__ __forceinline__ Tw<T> load_tables(C2<T>* sm, const TG* __restrict__ Wg, int t) {
     // sm: [512 + 32]; Wg: the compact table in global memory, same layout
     for (int i = t; i < kCoarse + kFine; i += kNT) sm[i] = C2<T>{(T)Wg[i].x, (T)Wg[i].y};
-    return Tw<T>{sm, sm + kCoarse};
+    if (t < kT128) {  // W128^(j q) = W512^(4 j q): exact table entries
+        const int q = t / 16 + 1, j = t % 16;
+        const TG w = Wg[(4 * j * q) & (kCoarse - 1)];
+        sm[kCoarse + kFine + t] = C2<T>{(T)w.x, (T)w.y};
+    }
+    return Tw<T>{sm, sm + kCoarse, sm + kCoarse + kFine};
 }
 
 // forward radix-8 pass on the shared array: sub-transform size M, L = M/8.  Butterfly u = t + 256 k of
@@ -213,7 +222,10 @@ __device__ __forceinline__ void fwd_pass8(C2<T>* a, const Tw<T>& W, int t) {
     constexpr int LP = L + L / 16;  // pad(base + r*L) == pad(base) + r*LP
     constexpr bool kInvariant = (kNT % L) == 0;
     C2<T> w[8];
-    if constexpr (kInvariant) twiddles8<kF / M>(W, (t % L) * (kF / M), w);
+    if constexpr (M == 128) {
+#pragma unroll
+        for (int q = 1; q < 8; q++) w[q] = W.t128[(q - 1) * 16 + (t % L)];
+    } else if constexpr (kInvariant) twiddles8<kF / M>(W, (t % L) * (kF / M), w);
 #pragma unroll 1
     for (int k = 0; k < kF / 8 / kNT; k++) {
         const int u = t + kNT * k, b = u / L, j = u % L, base = b * M + j;
@@ -234,7 +246,10 @@ __device__ __forceinline__ void inv_pass8(C2<T>* a, const Tw<T>& W, int t) {
     constexpr int LP = L + L / 16;
     constexpr bool kInvariant = (kNT % L) == 0;
     C2<T> w[8];
-    if constexpr (kInvariant) twiddles8<kF / M>(W, (t % L) * (kF / M), w);
+    if constexpr (M == 128) {
+#pragma unroll
+        for (int q = 1; q < 8; q++) w[q] = W.t128[(q - 1) * 16 + (t % L)];
+    } else if constexpr (kInvariant) twiddles8<kF / M>(W, (t % L) * (kF / M), w);
 #pragma unroll 1
     for (int k = 0; k < kF / 8 / kNT; k++) {
         const int u = t + kNT * k, b = u / L, j = u % L, base = b * M + j;
@@ -280,8 +295,10 @@ struct FftArgs {
     float divisor, post_nf;
     int c_begin, c_end;
     int n14, n13;          // per channel pair: n14 double segments (V14 outputs each), then n13 single segments (V13 each)
-    int n_items;           // pairs * (n14 + n13)
-    unsigned* work;        // [0] next item, [1] CTAs done
+    int n_items;           // pairs * (n14 + n13): all double segments first (the costly items), then the single ones
+    int n_heavy;           // pairs * n14
+    int stagger;           // start delay (cycles) per co-resident CTA slot, see fir_fft_kernel
+    unsigned* work;        // [0] next item, [1] CTAs done, [8 + smid] CTAs started on that SM
     float4* scratch;       // [gridDim.x][kF / 2] e' of the even half, in the last pass's own register order
 };
 
@@ -456,15 +473,28 @@ fir_fft_kernel(const __grid_constant__ FftArgs g) {
     const int t = threadIdx.x;
     const Tw<float> W = load_tables<float>(a + kPadded, g.Wg, t);
     float4* scr = g.scratch + (size_t)blockIdx.x * (kF / 2);
-    const int q = g.n14 + g.n13;
     const int V13 = kF - g.hist, V14 = 2 * kF - g.hist;
+    // Persistent CTAs that start together stay in lockstep (every item costs the same), so all three CTAs of an SM
+    // would sit in their global-load pass at the same time and in their FP passes at the same time.  The k-th CTA to
+    // start on an SM waits k * stagger cycles once, which spreads the load phases for the rest of the launch.
+    if (g.stagger > 0) {
+        if (t == 0) {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            const unsigned slot = atomicAdd(g.work + 8 + (smid & 255u), 1u) % 3u;
+            const long long t0 = clock64(), wait = (long long)slot * g.stagger;
+            while (clock64() - t0 < wait) __nanosleep(200);
+        }
+    }
     for (;;) {
         __syncthreads();  // the previous item's last pass has read the shared array (and s_item); tables visible
         if (t == 0) s_item = (int)atomicAdd(g.work, 1u);
         __syncthreads();
         const int item = s_item;
         if (item >= g.n_items) break;
-        const int pr = item / q, sg = item - pr * q;
+        int pr, sg;
+        if (item < g.n_heavy) { pr = item / g.n14; sg = item - pr * g.n14; }
+        else { const int li = item - g.n_heavy; pr = li / g.n13; sg = g.n14 + (li - pr * g.n13); }
         const int chA = g.c_begin + 2 * pr, chB = chA + 1;
         const bool hasB = chB < g.c_end;
         const bool dbl = sg < g.n14;
@@ -501,6 +531,7 @@ fir_fft_kernel(const __grid_constant__ FftArgs g) {
         if (atomicAdd(g.work + 1, 1u) == gridDim.x - 1) {
             g.work[0] = 0;
             g.work[1] = 0;
+            for (int i = 0; i < 256; i++) g.work[8 + i] = 0;
         }
     }
 }
@@ -879,7 +910,7 @@ int ensure_tables() {
 }
 
 constexpr int kMaxCtas = 3 * 192;  // persistent grid: 3 CTAs per SM, scratch slots sized for up to 192 SMs
-constexpr size_t kWorkHeader = 256;
+constexpr size_t kWorkHeader = 2048;  // [0] next, [1] done, [8 .. 264) per-SM start counters
 
 }  // namespace
 
@@ -935,7 +966,7 @@ int launch_fir_fft(const FirPlan& fp, const float* U, int64_t u_stride, float* Y
     if (!fp.fft_work) return (int)cudaErrorInvalidValue;
     static std::atomic<bool> configured_dev[kMaxDevices];
     std::atomic<bool>& configured = configured_dev[current_device_slot()];
-    const int smem = (kPadded + kCoarse + kFine) * (int)sizeof(float2);
+    const int smem = (kPadded + kTwEntries) * (int)sizeof(float2);
     if (!configured.load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(fir_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return (int)e;
@@ -963,6 +994,9 @@ int launch_fir_fft(const FirPlan& fp, const float* U, int64_t u_stride, float* Y
     const long long n_items = pairs * (g.n14 + g.n13);
     if (n_items <= 0 || n_items > (1ll << 30)) return (int)cudaErrorInvalidValue;
     g.n_items = (int)n_items;
+    g.n_heavy = (int)(pairs * g.n14);
+    static const int stagger_env = getenv("DSPB_FIR_STAGGER") ? atoi(getenv("DSPB_FIR_STAGGER")) : 12000;
+    g.stagger = stagger_env;
     g.work = reinterpret_cast<unsigned*>(fp.fft_work);
     g.scratch = reinterpret_cast<float4*>(reinterpret_cast<char*>(fp.fft_work) + kWorkHeader);
     const int grid = (int)std::min<long long>(n_items, std::min(kMaxCtas, 3 * g_tab.n_sm));
@@ -975,7 +1009,7 @@ int fir_prepare_spectrum(int log2F, const double* taps_rev_dev, int n_taps, floa
     if (log2F != kLog2F || n_taps > fir_fft_max_taps()) return (int)cudaErrorInvalidValue;
     int rc = ensure_tables();
     if (rc) return rc;
-    const int smem = (kPadded + kCoarse + kFine) * (int)sizeof(double2);
+    const int smem = (kPadded + kTwEntries) * (int)sizeof(double2);
     cudaError_t e = cudaFuncSetAttribute(fir_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     cudaStream_t st = (cudaStream_t)stream;
