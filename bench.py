@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--block", type=int, default=1024, help="device block (samples)")
     ap.add_argument("--blocks-per-step", type=int, default=16)
     ap.add_argument("--fir-mode", type=int, default=0)
+    ap.add_argument("--iir-mode", type=int, default=0, help="1 = opt-in time-parallel recurrences where the measured error allows (not bit-exact)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--sustain-seconds", type=float, default=2.0, help="length of the sustained section (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -186,7 +187,7 @@ def make_config(args, world, C_total, C_local, n):
     """The `config` object: identical for this repo's arm and the reference arm (same workload, same shape)."""
     return {"workload": args.workload, "scaling": args.scaling, "channels": C_total, "channels_per_gpu": C_local,
             "samples_per_step": n, "block": args.block, "blocks_per_step": args.blocks_per_step,
-            "fir_mode": FIR_MODES[args.fir_mode],
+            "fir_mode": FIR_MODES[args.fir_mode], "iir_mode": {0: "exact", 1: "scan_where_probe_passes"}[args.iir_mode],
             "l2_policy": f"inputs+outputs {2 * C_local * n * 4 / 2**20:.0f} MiB per step per GPU"
                          + (" exceed the 126 MB L2" if 2 * C_local * n * 4 > 126e6 else " (smaller than the 126 MB L2: see weak_scaling / N=1 for the L2-exceeding size)")}
 
@@ -366,7 +367,7 @@ def main():
     ch0, C_local, C_total = shard_of(args, rank, world, C)
     if C_local <= 0:
         raise SystemExit(f"rank {rank}: no channels to process ({C} channels over {world} ranks)")
-    eng = Engine(C_local, block=args.block, max_samples=n, device=local, fir_mode=args.fir_mode)
+    eng = Engine(C_local, block=args.block, max_samples=n, device=local, fir_mode=args.fir_mode, iir_mode=args.iir_mode)
     spec.apply(eng)
     n_in, n_out = eng._n_in, eng._n_out
 
@@ -492,7 +493,7 @@ def main():
         del eng
         xw = [torch.from_numpy(S.noise(C, n, seed=42 + i, channel_offset=rank * C)).cuda() for i in range(n_in)]
         yw = [torch.empty((C, n), dtype=torch.float32, device="cuda") for _ in range(n_out)]
-        engw = Engine(C, block=args.block, max_samples=n, device=local, fir_mode=args.fir_mode)
+        engw = Engine(C, block=args.block, max_samples=n, device=local, fir_mode=args.fir_mode, iir_mode=args.iir_mode)
         spec.apply(engw)
         for _ in range(warm):
             engw.process_device(xw, yw, n)

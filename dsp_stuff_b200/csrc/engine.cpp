@@ -263,6 +263,48 @@ void set_const_div(Op& op, int p_b, int p_r, float b, bool plan_only) {
     op.pad = ok ? 1 : 0;
 }
 
+// ---- opt-in time-parallel recurrences (dspb_config::iir_mode = 1) ---------------------------------------------------
+// ScanTab for y[n] = p[n] - a1 y[n-1] - a2 y[n-2]: powers of A = [[-a1, -a2], [1, 0]] in f64, rounded to f32.
+ScanTab make_scan_tab(float a1, float a2) {
+    ScanTab t;
+    memset(&t, 0, sizeof t);
+    t.a1 = a1;
+    t.a2 = a2;
+    double M[4] = {-(double)a1, -(double)a2, 1.0, 0.0}, R[4] = {1, 0, 0, 1};
+    auto mul2 = [](const double* a, const double* b, double* o) {
+        double r[4] = {a[0] * b[0] + a[1] * b[2], a[0] * b[1] + a[1] * b[3], a[2] * b[0] + a[3] * b[2], a[2] * b[1] + a[3] * b[3]};
+        memcpy(o, r, sizeof r);
+    };
+    for (int i = 0; i < 3; i++) mul2(M, M, M);  // A^8
+    memcpy(R, M, sizeof R);
+    for (int i = 0; i < 6; i++) {               // A^(8 * 2^i)
+        for (int k = 0; k < 4; k++) t.P[i][k] = R[k];
+        mul2(R, R, R);
+    }
+    return t;
+}
+// Verdict for one coefficient set: scan mode only if the device probe (fused_chain.cu measure_scan_error) stays below
+// half of the 1e-5 parity bar.  Cached per process (IEEE arithmetic: the same on every device).
+constexpr float kScanGate = 5e-6f;  // half of the 1e-5 parity bar: the probe sees ONE filter, a graph may chain several
+bool scan_qualifies(const Op& op, ScanTab& tab, bool plan_only) {
+    if (plan_only) { tab.probe_err = 0.0f; return true; }  // nothing runs in planning mode: show the optimistic schedule
+    static std::mutex mu;
+    static std::map<std::vector<uint32_t>, float> cache;
+    std::vector<uint32_t> key{op.code};
+    for (int i = 0; i < 4; i++) { uint32_t b; memcpy(&b, &op.p[i], 4); key.push_back(b); }
+    { uint32_t b; memcpy(&b, &op.a2, 4); key.push_back(b); }
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    float err = 1.0f;
+    if (it != cache.end()) err = it->second;
+    else {
+        if (measure_scan_error(op, tab, &err) != 0) err = 1.0f;
+        cache[key] = err;
+    }
+    tab.probe_err = err;
+    return err <= kScanGate;
+}
+
 // Reverb::refresh_seconds, nodes/reverb.rs:55-71.  Integer work: must match the reference exactly.
 int64_t reverb_delay(float seconds, int sample_rate, int granule) {
     float prod = seconds * (float)sample_rate;
@@ -317,6 +359,7 @@ struct Lowerer {
     std::map<std::pair<int, int>, int> use_step;  // last step that uses the value
     std::vector<int> node_step;                   // step index in which a node's ops are emitted
     std::set<int> fused_sinks;                    // output terminals written directly by a FIR step
+    std::vector<ScanTab> scan_tabs;               // scan tables of the current fused step (Op::mode = index + 1)
     std::string err;
 
     explicit Lowerer(dspb_engine& en) : e(en) {}
@@ -527,13 +570,33 @@ void Lowerer::close_fused() {
     P.n_ops = (int)ops.size();
     P.needs_tile = 0;
     int64_t min_ring = INT64_MAX;
-    bool has_rec = false;
+    bool has_rec = false, has_scan = false;
+    auto is_lin_rec = [](int c) { return c == OP_BIQUAD || c == OP_LP1 || c == OP_HP1; };
+    // Scan mode pays only when NO sequential recurrence is left in the segment (one exact chain bounds the kernel anyway,
+    // and the pipelined warp-specialised kernels only take exact recurrences): all or nothing per segment.
+    bool any_exact = false;
+    for (auto& o : ops) any_exact = any_exact || o.code == OP_ENVELOPE || (is_lin_rec(o.code) && o.mode == 0);
+    if (any_exact)
+        for (size_t i = 0; i < ops.size(); i++)
+            if (is_lin_rec(ops[i].code) && ops[i].mode != 0) {
+                ops[i].mode = 0;
+                txt[i] += "  [exact after all: another recurrence of this segment stays sequential]";
+            }
+    P.n_scan = 0;
     for (int i = 0; i < P.n_ops; i++) {
         P.ops[i] = ops[i];
         const int c = ops[i].code;
-        if (c == OP_BIQUAD || c == OP_LP1 || c == OP_HP1 || c == OP_ENVELOPE) { P.needs_tile = 1; has_rec = true; }
+        if (is_lin_rec(c) && ops[i].mode != 0) {
+            has_scan = true;
+            P.scan[P.n_scan] = scan_tabs[ops[i].mode - 1];
+            P.ops[i].mode = (uint8_t)(++P.n_scan);
+        } else if (c == OP_BIQUAD || c == OP_LP1 || c == OP_HP1 || c == OP_ENVELOPE) {
+            P.needs_tile = 1;
+            has_rec = true;
+        }
         if (c == OP_COMB) min_ring = std::min(min_ring, e.nodes[cur.ring_nodes[ops[i].aux & 0xff]]->D);
     }
+    scan_tabs.clear();
     // Tile geometry: G channels x S = 4096/G samples per CTA.  S may not exceed the shortest comb
     // delay (a tile must never read a ring slot it writes itself); recurrences run lane = channel,
     // so they want G large, but the grid wants >= ~1.7 CTAs per SM (148 SMs).
@@ -552,6 +615,11 @@ void Lowerer::close_fused() {
             G = 32;
             while (G > 1 && (C + G - 1) / G < 256) G >>= 1;
         }
+    }
+    if (has_scan && !has_rec) {
+        // every thread works time-parallel: fill the machine with CTAs (about two per SM), channels per CTA as needed
+        G = 1;
+        while (G < 32 && (C + G - 1) / G > 296) G <<= 1;
     }
     while ((int64_t)kTile / G > min_ring && G < 32) G <<= 1;
     if (e.force_G) G = e.force_G;
@@ -816,7 +884,7 @@ int Lowerer::lower() {
             default: {  // single-input effect nodes
                 Op op = mk(OP_END);
                 std::string desc;
-                char b[160];
+                char b[320];
                 switch (nd.type) {
                     case T_GAIN:
                         op.code = OP_GAIN;
@@ -846,18 +914,36 @@ int Lowerer::lower() {
                         snprintf(b, sizeof b, "acc = chebyshev(acc, %g, %g)", nd.f32[0], nd.f32[1]);
                         break;
                     case T_BIQUAD:
-                        op.code = OP_BIQUAD;
-                        for (int i = 0; i < 4; i++) op.p[i] = nd.bq[i];
-                        op.a2 = nd.bq[4];
-                        snprintf(b, sizeof b, "acc = DF1(acc; b=%g,%g,%g a=%g,%g) exact, lane=channel", nd.bq[0], nd.bq[1], nd.bq[2], nd.bq[3], nd.bq[4]);
-                        break;
                     case T_LOWPASS:
-                    case T_HIGHPASS:
-                        op.code = nd.type == T_LOWPASS ? OP_LP1 : OP_HP1;
-                        op.p[0] = nd.f32[0];
-                        op.p[1] = 1.0f - nd.f32[0];
-                        snprintf(b, sizeof b, "acc = %s(acc; ratio=%g) exact, lane=channel", nt.cfg_name, nd.f32[0]);
-                        break;
+                    case T_HIGHPASS: {
+                        ScanTab tab;
+                        if (nd.type == T_BIQUAD) {
+                            op.code = OP_BIQUAD;
+                            for (int i = 0; i < 4; i++) op.p[i] = nd.bq[i];
+                            op.a2 = nd.bq[4];
+                            tab = make_scan_tab(nd.bq[3], nd.bq[4]);
+                            snprintf(b, sizeof b, "acc = DF1(acc; b=%g,%g,%g a=%g,%g)", nd.bq[0], nd.bq[1], nd.bq[2], nd.bq[3], nd.bq[4]);
+                        } else {
+                            op.code = nd.type == T_LOWPASS ? OP_LP1 : OP_HP1;
+                            op.p[0] = nd.f32[0];
+                            op.p[1] = 1.0f - nd.f32[0];
+                            tab = make_scan_tab(-nd.f32[0], 0.0f);  // z[n] = xr[n] + ratio z[n-1]
+                            snprintf(b, sizeof b, "acc = %s(acc; ratio=%g)", nt.cfg_name, nd.f32[0]);
+                        }
+                        std::string how = " exact, lane=channel";
+                        if (e.cfg.iir_mode == 1) {
+                            char v[96];
+                            if ((int)scan_tabs.size() < kMaxScan && scan_qualifies(op, tab, e.plan_only)) {
+                                scan_tabs.push_back(tab);
+                                op.mode = (uint8_t)scan_tabs.size();
+                                snprintf(v, sizeof v, " time-parallel scan (probe error %.2g <= %.2g)", tab.probe_err, kScanGate);
+                            } else {
+                                snprintf(v, sizeof v, " exact, lane=channel (scan probe error %.2g > %.2g)", tab.probe_err, kScanGate);
+                            }
+                            how = v;
+                        }
+                        strncat(b, how.c_str(), sizeof b - strlen(b) - 1);
+                    } break;
                     case T_ENVELOPE:
                         op.code = OP_ENVELOPE;
                         op.p[0] = nd.f32[0] == 0.0f ? 0.0f : std::exp(-1.0f / nd.f32[0]);  // dasp calc_gain
@@ -1153,6 +1239,10 @@ int dspb_engine_create(const dspb_config* cfg, dspb_engine** out) {
     if (e->cfg.fir_mode < FIR_FFT || e->cfg.fir_mode > FIR_FFT_PACKED) {
         delete e;
         return fail(DSPB_ERR_INVALID, "fir_mode must be 0 (FFT), 1 (direct), 2 (Toeplitz tensor-core) or 3 (packed FFT)");
+    }
+    if (e->cfg.iir_mode < 0 || e->cfg.iir_mode > 1) {
+        delete e;
+        return fail(DSPB_ERR_INVALID, "iir_mode must be 0 (exact recurrences) or 1 (time-parallel scan where the measured error allows)");
     }
     if (const char* g = getenv("DSPB_FORCE_G")) e->force_G = atoi(g);
     if (const char* g = getenv("DSPB_CHUNKS")) e->dev_chunks = std::max(1, std::min(8, atoi(g)));

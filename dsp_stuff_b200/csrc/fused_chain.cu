@@ -21,9 +21,12 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "exact_math.cuh"
 #include "plan.h"
@@ -198,6 +201,76 @@ __device__ __forceinline__ void run_recurrence(Core core, float (&v)[kChunk], co
     }
 }
 
+// Time-parallel evaluation of y[n] = p[n] - a1 y[n-1] - a2 y[n-2] over one tile (opt-in, dspb_config::iir_mode = 1; see
+// plan.h ScanTab).  v holds this thread's 8 values of p on entry and of y on exit.  (1) every thread runs its chunk from a
+// zero state: the chunk's end state e; (2) Kogge-Stone scan of the end states over the lanes of the channel with the
+// strides A^(8 d), the state carried in from the previous tile (or from the warps in front) entering at lane 0;
+// (3) every thread re-runs its chunk from its true start state.  Steps (1) and (2) run in f64, step (3) in f32 with FMA:
+// the result is closer to exact filtering than the reference's own f32 evaluation, and it is NOT the reference's rounding.
+// ONEPOLE: the state is the single value z, kept in .x like the exact path keeps it (a ratio change may flip a filter between
+// the two evaluations without touching its state); else (y1, y2) in .z / .w.
+template <int G, bool ONEPOLE>
+__device__ __forceinline__ void scan_recurrence(const ScanTab& tab, float (&v)[kChunk], const TileCtx& tc, int j_last, float4* st,
+                                                double2* wend) {
+    constexpr int TPC = Geo<G>::TPC;
+    constexpr int W = TPC < 32 ? TPC : 32;   // lanes of one channel inside a warp
+    constexpr int NW = TPC / W;              // warps per channel
+    const double a1 = tab.a1, a2 = tab.a2;
+    const int li = tc.j % W, wi = tc.j / W;
+    double e1 = 0.0, e2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < kChunk; i++) {
+        const double y = fma(-a1, e1, fma(-a2, e2, (double)v[i]));
+        e2 = e1; e1 = y;
+    }
+    double c1 = ONEPOLE ? st[tc.g].x : st[tc.g].z, c2 = ONEPOLE ? 0.0f : st[tc.g].w;  // carried in from the previous tile
+    auto scan = [&](double s1, double s2) {
+#pragma unroll
+        for (int i = 0, d = 1; d < W; i++, d <<= 1) {
+            const double u1 = __shfl_up_sync(0xffffffffu, s1, d, W), u2 = __shfl_up_sync(0xffffffffu, s2, d, W);
+            if (li >= d) {
+                s1 = fma(tab.P[i][0], u1, fma(tab.P[i][1], u2, s1));
+                s2 = fma(tab.P[i][2], u1, fma(tab.P[i][3], u2, s2));
+            }
+        }
+        return make_double2(s1, s2);
+    };
+    if constexpr (NW > 1) {
+        const double2 z = scan(e1, e2);                // zero carry-in: the warp's own contribution
+        if (li == W - 1) wend[tc.g * NW + wi] = z;
+        __syncthreads();
+        for (int w = 0; w < wi; w++) {                 // carry into this warp: c <- E_w + A^256 c
+            const double2 E = wend[tc.g * NW + w];
+            const double n1 = fma(tab.P[5][0], c1, fma(tab.P[5][1], c2, E.x));
+            const double n2 = fma(tab.P[5][2], c1, fma(tab.P[5][3], c2, E.y));
+            c1 = n1; c2 = n2;
+        }
+    }
+    double s1 = e1, s2 = e2;
+    if (li == 0) {  // the carry enters at lane 0: its chunk end becomes e + A^8 c
+        s1 = fma(tab.P[0][0], c1, fma(tab.P[0][1], c2, e1));
+        s2 = fma(tab.P[0][2], c1, fma(tab.P[0][3], c2, e2));
+    }
+    const double2 S = scan(s1, s2);                    // true end state of every chunk
+    double q1 = __shfl_up_sync(0xffffffffu, S.x, 1, W), q2 = __shfl_up_sync(0xffffffffu, S.y, 1, W);
+    if (li == 0) { q1 = c1; q2 = c2; }
+    float p1 = (float)q1, p2 = (float)q2;
+    const float fa1 = tab.a1, fa2 = tab.a2;
+#pragma unroll
+    for (int i = 0; i < kChunk; i++) {
+        const float y = fmaf(-fa1, p1, fmaf(-fa2, p2, v[i]));
+        p2 = p1; p1 = y;
+        v[i] = y;
+    }
+    // every thread of the channel has read st by now (NW > 1: the barrier above; else one warp: __syncwarp)
+    if constexpr (NW == 1) __syncwarp();
+    if (tc.j == j_last) {
+        if constexpr (ONEPOLE) st[tc.g].x = (float)S.x;
+        else { st[tc.g].z = (float)S.x; st[tc.g].w = (float)S.y; }
+    }
+    if constexpr (NW > 1) __syncthreads();  // wend is free again (the next scan op of this tile rewrites it)
+}
+
 __device__ __forceinline__ void load16(const float4* s, int stride, float (&v)[kChunk]) {
 #pragma unroll
     for (int k = 0; k < kF4; k++) {
@@ -234,6 +307,7 @@ struct Ctx {
     const Program* prog;
     float4* sm_state;
     float2* edge;
+    double2* wend;  // [kThreads / 32] zero-carry end states of the warps (scan mode, channels wider than one warp)
     float4* stage;
     float4* vregs;
     TileCtx tc;
@@ -613,6 +687,13 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
                 acc[i] = add(add(mul(b0, xi), mul(b1, pm1)), mul(b2, pm2));
                 pm2 = pm1; pm1 = xi;
             }
+            if (mode != 0) {  // opt-in time-parallel evaluation (not bit-exact)
+                scan_recurrence<G, false>(prog.scan[mode - 1], acc, c.tc, c.j_last, st, c.wend);
+                // x1 / x2: read by the j == 0 thread of the channel right after the edge barrier above, i.e. before the
+                // barrier / __syncwarp inside scan_recurrence that every thread of the channel has passed by now
+                if (c.j == c.j_last) { st[c.g].x = nx1; st[c.g].y = nx2; }
+                break;
+            }
             DF1Core core;
             core.a1 = op.p[3];
             core.a2 = op.a2;
@@ -625,6 +706,12 @@ __device__ __forceinline__ void exec_op(const int code, const int mode, const in
             float v[kChunk];
 #pragma unroll
             for (int i = 0; i < kChunk; i++) v[i] = mul(acc[i], omr);
+            if (mode != 0) {  // z[n] = xr[n] + r z[n-1] as the scan with a1 = -r, a2 = 0; z lives in .z of the state (exact: .x)
+                scan_recurrence<G, true>(prog.scan[mode - 1], v, c.tc, c.j_last, c.sm_state + op.aux * G, c.wend);
+#pragma unroll
+                for (int i = 0; i < kChunk; i++) acc[i] = code == OP_LP1 ? v[i] : sub(acc[i], v[i]);
+                break;
+            }
             OnePoleCore core;
             core.r = op.p[0];
             run_recurrence<G>(core, v, c.tc, c.sm_state + op.aux * G);
@@ -737,6 +824,13 @@ struct ChainGDBR {  // src -> gain -> distort(SoftClip) -> biquad -> reverb -> s
     }
 };
 template <int PF>
+struct ChainGDBRScan {  // the same chain with the biquad in scan mode (dspb_config::iir_mode = 1, scan table 0)
+    static constexpr int n = 6;
+    [[maybe_unused]] static constexpr int rec = -1;
+    __host__ __device__ static constexpr int pf_of(int i) { return ChainGDBR<PF>::pf_of(i); }
+    __host__ __device__ static constexpr int sig(int i) { return i == 3 ? DSPB_SIG(OP_BIQUAD, 1, 7) : ChainGDBR<PF>::sig(i); }
+};
+template <int PF>
 struct ChainGDR {  // src -> gain -> distort(SoftClip) -> reverb -> store   (config 1)
     static constexpr int n = 5;
     [[maybe_unused]] static constexpr int rec = -1;
@@ -800,7 +894,8 @@ fused_kernel(const __grid_constant__ Program prog, int c_begin, int c_end, long 
     // shared memory carve-up
     c.sm_state = smem4;                                                  // [kMaxStates][G]
     c.edge = reinterpret_cast<float2*>(c.sm_state + kMaxStates * G);     // [kThreads] chunk-edge samples
-    float* tile = reinterpret_cast<float*>(c.edge + kThreads);
+    c.wend = reinterpret_cast<double2*>(c.edge + kThreads);              // [kThreads / 32] warp end states (scan mode)
+    float* tile = reinterpret_cast<float*>(c.wend + kThreads / 32);
     c.stage = reinterpret_cast<float4*>(tile + (prog.needs_tile ? G * Q::ROW : 0));  // (unused: prefetch lives in registers)
     c.vregs = c.stage;                                                               // [n_vregs][kF4][kThreads]
 
@@ -1012,6 +1107,7 @@ fused_kernel_ws(const __grid_constant__ Program prog, int c_begin, int c_end, lo
     c.T = (int)T;
     c.init_streams(prog);
     c.sm_state = nullptr;
+    c.wend = nullptr;
     c.edge = edge;
     c.stage = stage;
     c.vregs = stage;  // [n_vregs][kF4][kThreads]; none of them is live across the recurrence (ws_rec_index)
@@ -1283,6 +1379,7 @@ fused_kernel_ws2(const __grid_constant__ Program prog, int c_begin, int c_end, l
     c.T = T;
     c.init_streams(prog);
     c.sm_state = nullptr;
+    c.wend = nullptr;
     c.edge = edge;
     c.stage = nullptr;
     c.vregs = nullptr;
@@ -1577,6 +1674,7 @@ bool chain_matches(const Program& p) {
         const Op& o = p.ops[i];
         if (o.code != (s & 0xff) || o.pre != ((s >> 16) & 0xff) || o.pflags != 0) return false;
         if (o.code == OP_DISTORT && o.mode != ((s >> 8) & 0xff)) return false;
+        if ((o.code == OP_BIQUAD || o.code == OP_LP1 || o.code == OP_HP1) && o.mode != ((s >> 8) & 0xff)) return false;  // exact vs scan
         const bool is_src = o.code == OP_LOADG || o.code == OP_ADDG || o.code == OP_COPYG || o.code == OP_STOREG;
         const int has = is_src ? (o.aux != 0) : o.code == OP_COMB ? ((o.aux >> 8) != 0) : 0;
         if (has != Chain::pf_of(i)) return false;
@@ -1614,7 +1712,9 @@ int launch_gc(const Program& prog, int c_begin, int c_end, int64_t T, int n_stat
 template <int G>
 int launch_g(const Program& prog, int c_begin, int c_end, int64_t T, int n_states, cudaStream_t st) {
     static const bool no_static = getenv("DSPB_NO_STATIC") != nullptr;
-    static const bool no_ws = getenv("DSPB_NO_WS") != nullptr;
+    static const bool no_ws_env = getenv("DSPB_NO_WS") != nullptr;
+    // a recurrence in scan mode has no sequential part to hide: such programs take the plain kernel
+    const bool no_ws = no_ws_env || prog.n_scan > 0;
     {   // two recurrences in series: pipelined over two recurrence warps
         static const bool no_ws2 = getenv("DSPB_NO_WS2") != nullptr;
         int r1 = -1, r2 = -1;
@@ -1640,6 +1740,7 @@ int launch_g(const Program& prog, int c_begin, int c_end, int64_t T, int n_state
     }
     if (!no_static) {
         if (chain_matches<ChainGDBR<3>>(prog)) return launch_gc<G, ChainGDBR<3>>(prog, c_begin, c_end, T, n_states, st);
+        if (chain_matches<ChainGDBRScan<3>>(prog)) return launch_gc<G, ChainGDBRScan<3>>(prog, c_begin, c_end, T, n_states, st);
         if (chain_matches<ChainGDR<3>>(prog)) return launch_gc<G, ChainGDR<3>>(prog, c_begin, c_end, T, n_states, st);
         if (chain_matches<ChainGDR<1>>(prog)) return launch_gc<G, ChainGDR<1>>(prog, c_begin, c_end, T, n_states, st);
         if (chain_matches<ChainBB<1>>(prog)) return launch_gc<G, ChainBB<1>>(prog, c_begin, c_end, T, n_states, st);
@@ -1678,9 +1779,70 @@ int verify_const_div(float b, float r, unsigned long long* mismatches) {
     return (int)e;
 }
 
+// Probe for one recurrence: the same op in exact and in scan mode over 8 channels x 16384 samples (four of uniform noise,
+// four log sweeps 20 Hz - 20 kHz, amplitude 0.5), zero initial state; the result gates scan mode for this coefficient set.
+int measure_scan_error(const Op& exact_op, const ScanTab& tab, float* rel_err) {
+    constexpr int C = 8, G = 4;
+    constexpr int64_t T = 16384;
+    std::vector<float> x((size_t)C * T);
+    unsigned long long lcg = 0x9E3779B97F4A7C15ull;
+    for (int c = 0; c < C; c++)
+        for (int64_t n = 0; n < T; n++) {
+            float v;
+            if (c < 4) {
+                lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+                v = ((float)(int)((lcg >> 40) & 0xFFFFFF) - 8388608.0f) * (1.0f / 8388608.0f) * 0.5f;
+            } else {
+                const double t = (double)n / 48000.0, Ts = (double)T / 48000.0, k = std::log(1000.0);
+                v = (float)(0.5 * std::sin(2.0 * M_PI * 20.0 * Ts / k * (std::exp(t / Ts * k) - 1.0) + 0.7 * c));
+            }
+            x[(size_t)c * T + n] = v;
+        }
+    float *dx = nullptr, *dy = nullptr, *ds = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&dx, x.size() * 4)) != cudaSuccess) return (int)e;
+    if ((e = cudaMalloc(&dy, 2 * x.size() * 4)) != cudaSuccess) { cudaFree(dx); return (int)e; }
+    if ((e = cudaMalloc(&ds, 2 * C * 16)) != cudaSuccess) { cudaFree(dx); cudaFree(dy); return (int)e; }
+    cudaMemcpy(dx, x.data(), x.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemset(ds, 0, 2 * C * 16);
+    int rc = 0;
+    for (int m = 0; m < 2 && rc == 0; m++) {
+        Program P;
+        memset(&P, 0, sizeof P);
+        P.n_ops = 3;
+        P.ops[0].code = OP_LOADG; P.ops[0].buf = 0;
+        P.ops[1] = exact_op;
+        P.ops[1].pre = 0; P.ops[1].pflags = 0; P.ops[1].aux = 0; P.ops[1].mode = (uint8_t)m;
+        P.ops[2].code = OP_STOREG; P.ops[2].buf = 1;
+        P.needs_tile = m == 0;
+        P.n_scan = (int16_t)m;
+        P.scan[0] = tab;
+        P.bufs[0] = BufDesc{dx, T, 0, 0};
+        P.bufs[1] = BufDesc{dy + (size_t)m * C * T, T, 0, 0};
+        P.states[0] = ds + (size_t)m * C * 4;
+        for (int k = 0; k < kMaxPrefetch; k++) P.pf_buf[k] = P.pf_ring[k] = -1;
+        P.st_buf = -1;
+        rc = launch_fused(P, G, 0, C, T, nullptr);
+    }
+    std::vector<float> y(2 * x.size());
+    if (rc == 0) rc = (int)cudaMemcpy(y.data(), dy, y.size() * 4, cudaMemcpyDeviceToHost);
+    cudaFree(dx); cudaFree(dy); cudaFree(ds);
+    if (rc) return rc;
+    double peak = 0.0, err = 0.0;
+    bool finite = true;
+    for (size_t i = 0; i < x.size(); i++) {
+        const double a = y[i], b = y[x.size() + i];
+        finite = finite && std::isfinite(a) && std::isfinite(b);
+        peak = std::max(peak, std::fabs(a));
+        err = std::max(err, std::fabs(a - b));
+    }
+    *rel_err = (finite && peak > 0.0) ? (float)(err / peak) : 1.0f;  // an unstable filter never qualifies
+    return 0;
+}
+
 int fused_smem_bytes(const Program& prog, int G) {
     const int S = kTile / G;
-    size_t b = (size_t)kMaxStates * G * 16 + (size_t)kThreads * 8;
+    size_t b = (size_t)kMaxStates * G * 16 + (size_t)kThreads * 8 + (size_t)(kThreads / 32) * 16;
     if (prog.needs_tile) b += (size_t)G * (S + 4) * 4;
     b += (size_t)prog.n_vregs * kTile * 4;
     return (int)b;

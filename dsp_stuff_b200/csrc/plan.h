@@ -41,6 +41,7 @@ constexpr int kMaxBufs = 12;
 constexpr int kMaxRings = 6;
 constexpr int kMaxStates = 12;
 constexpr int kMaxPrefetch = 2;
+constexpr int kMaxScan = 4;         // recurrences of one fused segment that may run as a time-parallel scan
 
 enum OpCode : uint8_t {
     OP_END = 0,
@@ -73,9 +74,21 @@ enum OpCode : uint8_t {
 
 // Parameter source flags: bit i set => parameter Pi is a per-sample tile read from vreg pv[i]
 // (a connected `as_input` control port), else the scalar p[i].
+// Time-parallel ("scan") evaluation of a linear recurrence y[n] = p[n] - a1 y[n-1] - a2 y[n-2] (opt-in, NOT bit-exact:
+// dspb_config::iir_mode).  State s[n] = (y[n], y[n-1]) obeys s[n] = A s[n-1] + (p[n], 0), A = [[-a1, -a2], [1, 0]].
+// A thread owns kChunk = 8 consecutive samples; P[i] = A^(8 * 2^i) (row-major 2x2, f64) are the strides of the Kogge-Stone
+// scan over the lanes of a warp (i = 0..4) and over warps (i = 5: A^256).
+struct ScanTab {
+    double P[6][4];    // f64: the carried states are computed in double (plain DFMA, half the FP32 rate on B200), so the scan
+                       // itself adds ~1e-7; what is left against the reference is the reference's own f32 rounding
+    float a1, a2;
+    float probe_err;   // measured at dspb_compile: max |scan - exact| / max |exact| on the probe signal
+    float pad_;
+};
+
 struct Op {
     uint8_t code;
-    uint8_t mode;
+    uint8_t mode;     // DISTORT / SIGGEN: variant.  BIQUAD / LP1 / HP1: 0 = exact sequential evaluation, k > 0 = scan, table k - 1
     uint8_t pflags;
     uint8_t vreg;     // operand vreg for LOADV/ADDV/SAVEV/ADD/MIX
     uint8_t pv[3];    // vregs of tile-valued parameters
@@ -121,6 +134,8 @@ struct Program {
     int16_t pf_buf[kMaxPrefetch];
     int16_t pf_ring[kMaxPrefetch];
     int16_t st_buf;        // buffer of the first STOREG (its op has aux = 1): row pointer kept in a register, or -1
+    int16_t n_scan;        // scan tables in use
+    ScanTab scan[kMaxScan];
 };
 
 // ---- launchers (defined in the .cu files) -----------------------------------------------------------
@@ -129,6 +144,9 @@ int launch_fused(const Program& prog, int G, int c_begin, int c_end, int64_t T, 
 int fused_smem_bytes(const Program& prog, int G);
 // Enumerates all 2^32 dividends on the device; *mismatches == 0 proves div_const exact for divisor b.
 int verify_const_div(float b, float r, unsigned long long* mismatches);
+// Runs a one-recurrence probe program in exact and in scan mode on the device (noise + log sweep, 16384 samples) and
+// returns max |scan - exact| / max |exact|: the measured error that gates scan mode for one coefficient set.
+int measure_scan_error(const Op& exact_op, const ScanTab& tab, float* rel_err);
 // debug: summed clock64 phase timings of the warp-specialised kernel (only with -DDSPB_WS_TIMING)
 int ws_timing_read(long long* out8, bool clear);
 

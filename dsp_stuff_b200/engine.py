@@ -38,6 +38,7 @@ class Config(ctypes.Structure):
         ("max_samples", ctypes.c_int64),
         ("fir_fft_log2", ctypes.c_int32),
         ("fir_mode", ctypes.c_int32),
+        ("iir_mode", ctypes.c_int32),
     ]
 
 
@@ -101,12 +102,12 @@ class Engine:
     """One engine = one graph instantiated over `channels` mono streams on one GPU."""
 
     def __init__(self, channels: int, block: int = 128, max_samples: int = 0, ring_granule: int = 1024,
-                 device: int = 0, fir_mode: int = FIR_FFT, sample_rate: int = 48000):
+                 device: int = 0, fir_mode: int = FIR_FFT, sample_rate: int = 48000, iir_mode: int = 0):
         self._L = load_library()
         self.channels = channels
         self.device = device
         cfg = Config(channels=channels, block=block, sample_rate=sample_rate, ref_block=128, ring_granule=ring_granule,
-                     device=device, max_samples=max_samples, fir_fft_log2=0, fir_mode=fir_mode)
+                     device=device, max_samples=max_samples, fir_fft_log2=0, fir_mode=fir_mode, iir_mode=iir_mode)
         h = ctypes.c_void_p()
         self._h = None
         self._ck(self._L.dspb_engine_create(ctypes.byref(cfg), ctypes.byref(h)))

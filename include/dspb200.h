@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define DSPB_ABI_VERSION 1
+#define DSPB_ABI_VERSION 2
 
 typedef enum dspb_status {
     DSPB_OK = 0,
@@ -66,6 +66,16 @@ typedef struct dspb_config {
                              2 -> Toeplitz-tiled tensor-core GEMM (tcgen05, split bf16 operands, f32 accumulate;
                              the comparison path of BASELINE config 4, within the 1e-5 parity bar);
                              3 -> experimental FFT variant carrying two sub-transforms per f32x2 register pair */
+    int32_t iir_mode;     /* 0 -> every recurrence (biquad.rs:87, low_pass.rs:36-39, high_pass.rs:36-39) is evaluated strictly
+                             sequentially in the reference's operation order: bit-identical, but a launch with few channels
+                             is bound by the 12-cycle dependent chain per sample.
+                             1 -> opt-in time-parallel evaluation (chunked zero-state responses + a warp-shuffle scan of the
+                             2x2 state transition over the block, FMA): NOT bit-exact.  It is enabled PER FILTER only when
+                             the error measured at dspb_compile on a probe signal (scan vs exact, on the device) is below
+                             5e-6 of the output peak, half of the 1e-5 parity bar (with the carried states computed in f64
+                             the scan is closer to exact filtering than the reference's own f32 evaluation, so what the
+                             probe measures is essentially the reference's rounding error); a filter that fails the probe
+                             (e.g. a 200 Hz high-pass in f32) keeps the exact path.  dspb_describe_plan shows the verdicts. */
 } dspb_config;
 
 /* ---- lifetime ----------------------------------------------------------------------------- */

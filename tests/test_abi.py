@@ -34,15 +34,15 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_version(lib):
-    assert lib.dspb_abi_version() == 1
+    assert lib.dspb_abi_version() == 2
 
 
 def test_config_struct_matches_header():
     from dsp_stuff_b200 import engine
 
-    assert ctypes.sizeof(engine.Config) == 6 * 4 + 8 + 2 * 4
+    assert ctypes.sizeof(engine.Config) == 6 * 4 + 8 + 4 * 4   # 3 x int32 + tail padding to the int64 alignment
     assert [f[0] for f in engine.Config._fields_] == ["channels", "block", "sample_rate", "ref_block", "ring_granule",
-                                                     "device", "max_samples", "fir_fft_log2", "fir_mode"]
+                                                     "device", "max_samples", "fir_fft_log2", "fir_mode", "iir_mode"]
 
 
 def test_engine_fails_loudly_without_gpu(lib):
