@@ -59,6 +59,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-block-calls", action="store_true")
+    ap.add_argument("--no-scan-side", action="store_true", help="skip the iir_mode=1 side measurement")
     ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaling side measurement of a strong N>1 run")
     ap.add_argument("--gather", action="store_true", help="also time an NCCL gather of the outputs to rank 0")
     return ap.parse_args()
@@ -487,6 +488,28 @@ def main():
         barrier()
         gather_ms = g0.elapsed_time(g1)
 
+    # ---- opt-in scan mode (iir_mode 1) next to the bit-exact default: same shard, same input ------------------------
+    scan_side = None
+    if args.iir_mode == 0 and not args.no_scan_side and any(nd.typename in ("biquad", "low_pass", "high_pass") for nd in spec.nodes):
+        engs = Engine(C_local, block=args.block, max_samples=n, device=local, fir_mode=args.fir_mode, iir_mode=1)
+        spec.apply(engs)
+        verdicts = [ln.strip() for ln in engs.describe_plan().splitlines() if "scan" in ln and ("DF1(" in ln or "_pass(" in ln)]
+        for _ in range(warm):
+            engs.process_device(x_dev, y_dev, n)
+        sms = timed_steps(engs, x_dev, y_dev, n, args.steps, stream, barrier)
+        (sms,) = allmax([sms])
+        sp = None
+        if rank == 0 and not args.no_parity:
+            try:
+                sp = parity_check(args, spec, engs, x_dev, n, ch0)
+            except Exception as ex:  # noqa: BLE001
+                sp = {"pass": False, "error": str(ex)[:200]}
+        barrier()
+        scan_side = {"value": float(C_total) * n * args.steps / (sms * 1e-3), "unit": UNIT, "ms_per_step": sms / args.steps,
+                     "iir_mode": "scan_where_probe_passes (opt-in, not bit-exact)", "filters": [v[:160] for v in verdicts],
+                     "parity_check": sp}
+        del engs
+
     # ---- weak-scaling side measurement of a strong run: every GPU takes the full channel count ---------------------
     weak = None
     if world > 1 and args.scaling == "strong" and not args.no_weak:
@@ -556,6 +579,8 @@ def main():
             line["block_calls"] = block_calls
         if parity is not None:
             line["parity_check"] = parity
+        if scan_side:
+            line["scan_mode"] = scan_side
         if weak:
             line["weak_scaling"] = weak
         if not args.no_e2e:

@@ -88,7 +88,17 @@ __device__ __forceinline__ void static_for(Fn&& f) {
     static_for_impl<N>(static_cast<Fn&&>(f), std::make_integer_sequence<int, N>{});
 }
 
-// a * w_SZ^I  (forward: w = exp(-2 pi i / SZ); INV: conjugate), I < SZ/2, SZ in {2,4,8,16}
+// cos / sin of 2 pi m / 32 as compile-time constants
+__host__ __device__ constexpr double cos32(int m) {
+    constexpr double tab[9] = {1.0, 0.98078528040323044913, 0.92387953251128675613, 0.83146961230254523708, 0.70710678118654752440,
+                               0.55557023301960222474, 0.38268343236508977173, 0.19509032201612826785, 0.0};
+    m = ((m % 32) + 32) % 32;
+    if (m > 16) m = 32 - m;
+    return m > 8 ? -tab[16 - m] : tab[m];
+}
+__host__ __device__ constexpr double sin32(int m) { return cos32(m - 8); }
+
+// a * w_SZ^I  (forward: w = exp(-2 pi i / SZ); INV: conjugate), I < SZ/2, SZ in {2,4,8,16,32}
 template <int SZ, int I, bool INV, typename T>
 __device__ __forceinline__ C2<T> tw(C2<T> a) {
     if constexpr (I == 0) {
@@ -105,10 +115,8 @@ __device__ __forceinline__ C2<T> tw(C2<T> a) {
         if constexpr (INV) return {-(a.x + a.y) * h, (a.x - a.y) * h};
         else return {(a.y - a.x) * h, -(a.x + a.y) * h};
     } else {
-        static_assert(SZ == 16, "generic twiddles are only tabulated for SZ = 16");
-        constexpr double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173;
-        constexpr double cs[4][2] = {{c1, s1}, {s1, c1}, {-s1, c1}, {-c1, s1}};  // I = 1, 3, 5, 7
-        const T c = T(cs[(I - 1) / 2][0]), s = T(cs[(I - 1) / 2][1]);
+        static_assert(SZ == 16 || SZ == 32, "generic twiddles are tabulated for SZ = 16 and 32");
+        const T c = T(cos32(I * (32 / SZ))), s = T(sin32(I * (32 / SZ)));
         if constexpr (INV) return {a.x * c - a.y * s, a.y * c + a.x * s};
         else return {a.x * c + a.y * s, a.y * c - a.x * s};
     }
@@ -117,7 +125,7 @@ __device__ __forceinline__ C2<T> tw(C2<T> a) {
 // in-register radix-2 decimation-in-frequency DFT of R points: natural in, bit-reversed out
 template <int R, typename T>
 __device__ __forceinline__ void fft_dif(C2<T> (&v)[R]) {
-    static_for<4>([&](auto st) {
+    static_for<5>([&](auto st) {
         constexpr int sz = R >> decltype(st)::value;
         if constexpr (sz >= 2) {
             constexpr int half = sz / 2;
@@ -135,7 +143,7 @@ __device__ __forceinline__ void fft_dif(C2<T> (&v)[R]) {
 // exact mirror: bit-reversed in, natural out, conjugate twiddles, unnormalised (gain R)
 template <int R, typename T>
 __device__ __forceinline__ void ifft_dit(C2<T> (&v)[R]) {
-    static_for<4>([&](auto st) {
+    static_for<5>([&](auto st) {
         constexpr int sz = 2 << decltype(st)::value;
         if constexpr (sz <= R) {
             constexpr int half = sz / 2;
@@ -152,6 +160,8 @@ __device__ __forceinline__ void ifft_dit(C2<T> (&v)[R]) {
 }
 
 __host__ __device__ constexpr int bitrev3(int s) { return ((s & 1) << 2) | (s & 2) | ((s >> 2) & 1); }
+__host__ __device__ constexpr int bitrev4(int s) { return ((s & 1) << 3) | ((s & 2) << 1) | ((s & 4) >> 1) | ((s >> 3) & 1); }
+__host__ __device__ constexpr int bitrev5(int s) { return ((s & 1) << 4) | ((s & 2) << 2) | (s & 4) | ((s & 8) >> 2) | ((s >> 4) & 1); }
 __device__ __forceinline__ int pad(int p) { return p + (p >> 4); }
 
 // Twiddle source.  W16384^n = coarse[n >> 5] * fine[n & 31] with coarse[m] = exp(-2 pi i m / 512) (512 entries) and
@@ -295,6 +305,7 @@ struct FftArgs {
     float divisor, post_nf;
     int c_begin, c_end;
     int n14, n13;          // per channel pair: n14 double segments (V14 outputs each), then n13 single segments (V13 each)
+    long long single_base; // first output sample of the single segments (= double segments in front * V14, whoever ran them)
     int n_items;           // pairs * (n14 + n13): all double segments first (the costly items), then the single ones
     int n_heavy;           // pairs * n14
     int stagger;           // start delay (cycles) per co-resident CTA slot, see fir_fft_kernel
@@ -498,7 +509,7 @@ fir_fft_kernel(const __grid_constant__ FftArgs g) {
         const int chA = g.c_begin + 2 * pr, chB = chA + 1;
         const bool hasB = chB < g.c_end;
         const bool dbl = sg < g.n14;
-        const long long s0 = dbl ? (long long)sg * V14 : (long long)g.n14 * V14 + (long long)(sg - g.n14) * V13;
+        const long long s0 = dbl ? (long long)sg * V14 : g.single_base + (long long)(sg - g.n14) * V13;
         const long long w0 = s0 - g.hist;                      // call-relative index of window sample 0 (>= -hist)
         const int win = dbl ? 2 * kF : kF;
         const long long lim_ll = g.T - w0;                     // window samples >= lim lie beyond this call's input: zeros
@@ -534,6 +545,235 @@ fir_fft_kernel(const __grid_constant__ FftArgs g) {
             for (int i = 0; i < 256; i++) g.work[8 + i] = 0;
         }
     }
+}
+
+// ======================= 16384-point segments in one piece ("wide" kernel) =======================
+// The double segments above cost 2.9 single ones (measured): two sub-transforms, each with all six shared-memory round
+// trips of the 8192-point pipeline, which is what bounds that kernel (ncu: l1tex data pipe 69 % busy, 79 % of it shared
+// memory).  This kernel keeps a whole 16384-point transform of a channel pair in shared memory (139 KB, one 512-thread
+// CTA per SM, 128 registers per thread) with radices 16 . 32 . 32: FOUR shared-memory round trips per transform instead of
+// six, on 16384 points that yield 12288 outputs per channel instead of 8192 points that yield 4096.
+//   pass 1   global -> radix 16 over stride 1024 -> twiddle W16384^(j k) -> shared
+//   pass 2   radix 32 over stride 32 inside each 1024-block -> twiddle W1024^(j k) (table in shared memory) -> shared
+//   middle   radix 32 over 32 contiguous points . spectrum product . inverse radix 32, in registers
+//   pass 2', pass 1' mirror images; pass 1' writes the 12288 valid outputs of both channels to global memory
+// Output position p = k1 * 1024 + k2 * 32 + s holds bin f = k1 + 16 k2 + 512 bitrev5(s); the spectrum table is computed
+// directly in that order (fir_spectrum_wide_kernel).  Layout: p + 2 (p >> 5): every access pattern above is
+// conflict-free (the middle pass moves two complex values per 128-bit access).  Persistent: one CTA per SM fetches
+// (channel pair, segment) items from an atomic counter and prefetches the next item's window into L2 while it computes.
+constexpr int kN2 = 2 * kF;                 // 16384
+constexpr int kNTW = 512;                   // threads
+constexpr int kPadW = kN2 + kN2 / 16;       // 17408 complex
+constexpr int kT2 = 31 * 32;                // W1024^(j k), k = 1..31 major, j < 32
+constexpr int kTwW = kCoarse + kFine + kT2; // table entries in shared memory
+__device__ __forceinline__ int padw(int p) { return p + ((p >> 5) << 1); }
+
+struct WideArgs {
+    const float* U;
+    long long u_stride;
+    int u_ring, u_pos, hist;
+    float* Y;
+    long long y_stride;
+    const float4* Hw;      // [16][8192] float4: (H[32 u + 2 q], H[32 u + 2 q + 1]) at [q * 512 ... ] per 512-thread round, see mid pass
+    const float2* Wg;      // compact twiddle table [512 + 32] followed by the W1024 table [31 * 32]
+    float divisor, post_nf;
+    int c_begin, c_end;
+    int n14;               // double segments per channel pair (all lie fully inside the call)
+    int n_items;           // pairs * n14
+    unsigned* work;        // [2] next item, [3] CTAs done  (slots 0 / 1 belong to the narrow kernel on the same lane)
+};
+
+__global__ void __launch_bounds__(kNTW, 1)
+fir_fft_wide_kernel(const __grid_constant__ WideArgs g) {
+    extern __shared__ float2 smem_f2[];
+    __shared__ int s_item[2];
+    C2<float>* a = reinterpret_cast<C2<float>*>(smem_f2);
+    C2<float>* tabs = a + kPadW;
+    const int t = threadIdx.x;
+    for (int i = t; i < kTwW; i += kNTW) tabs[i] = C2<float>{g.Wg[i].x, g.Wg[i].y};
+    const Tw<float> W{tabs, tabs + kCoarse, nullptr};
+    const C2<float>* T2 = tabs + kCoarse + kFine;   // [(k - 1) * 32 + j]
+    const int V14 = kN2 - g.hist;
+    const bool post = g.post_nf != 0.0f;
+    const float post_rnf = post ? __frcp_rn(g.post_nf) : 0.0f;
+    auto fin = [&](float y) {
+        y = __fmul_rn(y, g.divisor);
+        return post ? div_nf(y, g.post_nf, post_rnf) : y;
+    };
+    if (t == 0) s_item[0] = (int)atomicAdd(g.work + 2, 1u);
+    __syncthreads();
+    for (int it = 0;; it++) {
+        const int item = s_item[it & 1];
+        if (item >= g.n_items) break;
+        if (t == 0) s_item[(it + 1) & 1] = (int)atomicAdd(g.work + 2, 1u);  // the next item: known one item ahead (L2 prefetch)
+        const int pr = item / g.n14, sg = item - pr * g.n14;
+        const int chA = g.c_begin + 2 * pr, chB = chA + 1;
+        const bool hasB = chB < g.c_end;
+        const long long w0 = (long long)sg * V14 - g.hist;          // call-relative index of window sample 0
+        const int wb = ring_slot(g.u_pos, (int)w0, g.u_ring);       // its ring slot; the window holds kN2 <= u_ring samples
+        const float* rowA = g.U + (long long)chA * g.u_stride;
+        const float* rowB = g.U + (long long)(hasB ? chB : chA) * g.u_stride;
+        const bool nowrap = wb + kN2 <= g.u_ring;
+
+        // ---- pass 1: global -> radix 16 -> shared
+#pragma unroll 1
+        for (int k = 0; k < 2; k++) {
+            const int j = t + kNTW * k;
+            C2<float> v[16];
+            if (nowrap) {
+                const float* pa = rowA + wb + j;
+                const float* pb = rowB + wb + j;
+#pragma unroll
+                for (int r = 0; r < 16; r++) v[r] = C2<float>{__ldg(pa + r * 1024), __ldg(pb + r * 1024)};
+            } else {
+#pragma unroll
+                for (int r = 0; r < 16; r++) {
+                    int sl = wb + j + r * 1024;
+                    if (sl >= g.u_ring) sl -= g.u_ring;
+                    v[r] = C2<float>{__ldg(rowA + sl), __ldg(rowB + sl)};
+                }
+            }
+            fft_dif<16>(v);
+            // twiddles W16384^(j q): w1, w2, w4, w8 from the table, the rest by products
+            C2<float> w[16];
+            w[1] = W.at2(j); w[2] = W.at2(2 * j); w[4] = W.at2(4 * j); w[8] = W.at2(8 * j);
+            w[3] = cmul(w[1], w[2]); w[5] = cmul(w[1], w[4]); w[6] = cmul(w[2], w[4]); w[7] = cmul(w[3], w[4]);
+#pragma unroll
+            for (int q = 9; q < 16; q++) w[q] = cmul(w[q - 8], w[8]);
+            C2<float>* p = a + padw(j);   // padw(j + 1024 q) = padw(j) + 1088 q
+            p[0] = v[0];
+#pragma unroll
+            for (int s = 1; s < 16; s++) p[bitrev4(s) * 1088] = cmul(v[s], w[bitrev4(s)]);
+        }
+        __syncthreads();
+        // L2 prefetch of the next item's window (the counter was fetched one item ahead)
+        {
+            const int nxt = s_item[(it + 1) & 1];
+            if (nxt < g.n_items) {
+                const int npr = nxt / g.n14, nsg = nxt - npr * g.n14;
+                const int nA = g.c_begin + 2 * npr;
+                const int nwb = ring_slot(g.u_pos, (int)((long long)nsg * V14 - g.hist), g.u_ring);
+                // 2 rows x 16384 floats = 1024 lines of 128 bytes: two per thread
+                const int line = t & 511, row = 0;
+                (void)row;
+                int sl = nwb + line * 32;
+                if (sl >= g.u_ring) sl -= g.u_ring;
+                const float* q0 = g.U + (long long)nA * g.u_stride + sl;
+                const float* q1 = g.U + (long long)(nA + 1 < g.c_end ? nA + 1 : nA) * g.u_stride + sl;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(q0));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(q1));
+            }
+        }
+        // ---- pass 2: radix 32 over stride 32 inside each 1024-block
+        {
+            const int b = t >> 5, j = t & 31;
+            C2<float>* p = a + padw(b * 1024 + j);   // padw(base + 32 r) = padw(base) + 34 r
+            C2<float> v[32];
+#pragma unroll
+            for (int r = 0; r < 32; r++) v[r] = p[r * 34];
+            fft_dif<32>(v);
+            p[0] = v[0];
+#pragma unroll
+            for (int s = 1; s < 32; s++) p[bitrev5(s) * 34] = cmul(v[s], T2[(bitrev5(s) - 1) * 32 + j]);
+        }
+        // Pass 2, the middle pass and pass 2' of 1024-block b all run on warp b (threads 32 b .. 32 b + 31 own both the
+        // butterflies b * 1024 + j + 32 r and the points 32 t .. 32 t + 31 of that block): warp-level synchronisation is
+        // enough, so the 16 warps drift apart over three quarters of the item instead of marching in lockstep.
+        __syncwarp();
+        // ---- middle: radix 32 on contiguous points . spectrum . inverse radix 32
+        {
+            float4* p4 = reinterpret_cast<float4*>(a + padw(32 * t));   // 32 contiguous points, no pad inside, 16-byte aligned
+            const float4* h4 = g.Hw + t;
+            C2<float> v[32];
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const float4 x = p4[q];
+                v[2 * q] = C2<float>{x.x, x.y};
+                v[2 * q + 1] = C2<float>{x.z, x.w};
+            }
+            fft_dif<32>(v);
+#pragma unroll
+            for (int q = 0; q < 16; q++) {
+                const float4 h = __ldg(h4 + q * kNTW);
+                v[2 * q] = cmul(v[2 * q], C2<float>{h.x, h.y});
+                v[2 * q + 1] = cmul(v[2 * q + 1], C2<float>{h.z, h.w});
+            }
+            ifft_dit<32>(v);
+#pragma unroll
+            for (int q = 0; q < 16; q++) p4[q] = make_float4(v[2 * q].x, v[2 * q].y, v[2 * q + 1].x, v[2 * q + 1].y);
+        }
+        __syncwarp();
+        // ---- pass 2': inverse radix 32 over stride 32
+        {
+            const int b = t >> 5, j = t & 31;
+            C2<float>* p = a + padw(b * 1024 + j);
+            C2<float> v[32];
+            v[0] = p[0];
+#pragma unroll
+            for (int s = 1; s < 32; s++) v[s] = cmulc(p[bitrev5(s) * 34], T2[(bitrev5(s) - 1) * 32 + j]);
+            ifft_dit<32>(v);
+#pragma unroll
+            for (int r = 0; r < 32; r++) p[r * 34] = v[r];
+        }
+        __syncthreads();
+        // ---- pass 1': inverse radix 16 over stride 1024 -> the valid outputs (window index >= hist) to global memory
+        {
+            float* outA = g.Y + (long long)chA * g.y_stride + w0;
+            float* outB = g.Y + (long long)(hasB ? chB : chA) * g.y_stride + w0;
+#pragma unroll 1
+            for (int k = 0; k < 2; k++) {
+                const int j = t + kNTW * k;
+                C2<float> w[16];
+                w[1] = W.at2(j); w[2] = W.at2(2 * j); w[4] = W.at2(4 * j); w[8] = W.at2(8 * j);
+                w[3] = cmul(w[1], w[2]); w[5] = cmul(w[1], w[4]); w[6] = cmul(w[2], w[4]); w[7] = cmul(w[3], w[4]);
+#pragma unroll
+                for (int q = 9; q < 16; q++) w[q] = cmul(w[q - 8], w[8]);
+                const C2<float>* p = a + padw(j);
+                C2<float> v[16];
+                v[0] = p[0];
+#pragma unroll
+                for (int s = 1; s < 16; s++) v[s] = cmulc(p[bitrev4(s) * 1088], w[bitrev4(s)]);
+                ifft_dit<16>(v);
+#pragma unroll
+                for (int r = 0; r < 16; r++) {
+                    const int n = j + r * 1024;
+                    if (n >= g.hist) {
+                        outA[n] = fin(v[r].x);
+                        if (hasB) outB[n] = fin(v[r].y);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // the shared array (and s_item[(it + 1) & 1]) are free / visible for the next item
+    }
+    if (t == 0) {
+        __threadfence();
+        if (atomicAdd(g.work + 3, 1u) == gridDim.x - 1) {
+            g.work[2] = 0;
+            g.work[3] = 0;
+        }
+    }
+}
+
+// Spectrum for the wide kernel: H16384[f] / 16384 by direct f64 summation (exact argument reduction), stored where the
+// middle pass of thread u finds it: float4 [q * 512 + u] = (H[f(32 u + 2 q)], H[f(32 u + 2 q + 1)]),
+// f(p) = k1 + 16 k2 + 512 bitrev5(s) for p = k1 * 1024 + k2 * 32 + s.
+__global__ void fir_spectrum_wide_kernel(const double* __restrict__ taps_rev, int N, float2* __restrict__ Hout) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= kN2) return;
+    const int k1 = p >> 10, k2 = (p >> 5) & 31, sreg = p & 31;
+    const int f = k1 + 16 * k2 + 512 * bitrev5(sreg);
+    double re = 0.0, im = 0.0;
+    for (int n = 0; n < N; n++) {
+        const int m = (int)(((long long)f * n) & (kN2 - 1));
+        double sn, cs;
+        sincospi(-2.0 * (double)m / (double)kN2, &sn, &cs);
+        const double h = taps_rev[N - 1 - n];  // h[n] = taps[N-1-n] (fir.rs:163-168)
+        re += h * cs;
+        im += h * sn;
+    }
+    const int u = p >> 5, q = sreg >> 1;
+    Hout[(size_t)(q * kNTW + u) * 2 + (sreg & 1)] = make_float2((float)(re / kN2), (float)(im / kN2));
 }
 
 // ======================= packed variant: two sub-transforms per register pair =======================
@@ -885,11 +1125,17 @@ std::mutex g_tab_mu;
 int ensure_tables() {
     std::lock_guard<std::mutex> lk(g_tab_mu);
     if (g_tab.Wf) return 0;
-    constexpr int n = kCoarse + kFine;
+    constexpr int n = kTwW;  // coarse | fine | W1024^(j k) table of the wide kernel
     std::vector<float2> wf(n);
     std::vector<double2> wd(n);
     for (int k = 0; k < n; k++) {
-        const double ang = k < kCoarse ? -2.0 * M_PI * (double)k / (double)kCoarse : -2.0 * M_PI * (double)(k - kCoarse) / (2.0 * kF);
+        double ang;
+        if (k < kCoarse) ang = -2.0 * M_PI * (double)k / (double)kCoarse;
+        else if (k < kCoarse + kFine) ang = -2.0 * M_PI * (double)(k - kCoarse) / (2.0 * kF);
+        else {
+            const int e = k - kCoarse - kFine, q = e / 32 + 1, j = e % 32;
+            ang = -2.0 * M_PI * (double)((j * q) & 1023) / 1024.0;
+        }
         wd[k] = make_double2(std::cos(ang), std::sin(ang));
         wf[k] = make_float2((float)wd[k].x, (float)wd[k].y);
     }
@@ -915,7 +1161,7 @@ constexpr size_t kWorkHeader = 2048;  // [0] next, [1] done, [8 .. 264) per-SM s
 }  // namespace
 
 int fir_fft_max_taps() { return kF / 2 + 1; }
-size_t fir_fft_spectrum_bytes() { return (size_t)4 * kF * sizeof(float2); }  // H13 | packed-kernel order | H14 even | H14 odd
+size_t fir_fft_spectrum_bytes() { return (size_t)6 * kF * sizeof(float2); }  // H13 | packed-kernel order | H14 even | H14 odd | wide (2 F)
 size_t fir_fft_work_bytes() { return kWorkHeader + (size_t)kMaxCtas * (kF / 2) * sizeof(float4); }
 static int effective_taps(int n) { return (n - 1 + 3) / 4 * 4 + 1; }  // Ne - 1 multiple of 4
 
@@ -991,13 +1237,44 @@ int launch_fir_fft(const FirPlan& fp, const float* U, int64_t u_stride, float* Y
     g.c_end = c_end;
     segment_plan(g.hist, T, &g.n14, &g.n13);
     const long long pairs = (c_end - c_begin + 1) / 2;
+    g.single_base = (long long)g.n14 * (2 * kF - g.hist);
+    g.work = reinterpret_cast<unsigned*>(fp.fft_work);
+    // Double segments: the wide kernel (a 16384-point transform in one piece, one CTA per SM); DSPB_FIR_WIDE=0 keeps them
+    // in the narrow kernel as two 8192-point sub-transforms.
+    static const bool wide_on = !(getenv("DSPB_FIR_WIDE") && atoi(getenv("DSPB_FIR_WIDE")) == 0);
+    if (wide_on && g.n14 > 0) {
+        static std::atomic<bool> wconf_dev[kMaxDevices];
+        std::atomic<bool>& wconf = wconf_dev[current_device_slot()];
+        const int wsmem = (kPadW + kTwW) * (int)sizeof(float2);
+        if (!wconf.load(std::memory_order_acquire)) {
+            cudaError_t e = cudaFuncSetAttribute(fir_fft_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wsmem);
+            if (e != cudaSuccess) return (int)e;
+            wconf.store(true, std::memory_order_release);
+        }
+        WideArgs w;
+        w.U = U; w.u_stride = u_stride; w.u_ring = fp.u_ring; w.u_pos = fp.u_pos; w.hist = g.hist;
+        w.Y = Y; w.y_stride = y_stride;
+        w.Hw = reinterpret_cast<const float4*>(fp.H + 4 * kF);
+        w.Wg = g_tab.Wf;
+        w.divisor = fp.divisor; w.post_nf = fp.post_nf;
+        w.c_begin = c_begin; w.c_end = c_end;
+        w.n14 = g.n14;
+        const long long wi = pairs * g.n14;
+        if (wi > (1ll << 30)) return (int)cudaErrorInvalidValue;
+        w.n_items = (int)wi;
+        w.work = g.work;
+        const int wgrid = (int)std::min<long long>(wi, g_tab.n_sm);
+        fir_fft_wide_kernel<<<wgrid, kNTW, wsmem, st>>>(w);
+        if (n_launches) *n_launches += 1;
+        g.n14 = 0;  // the narrow kernel below only runs the single segments behind single_base
+        if (g.n13 == 0) return (int)cudaGetLastError();
+    }
     const long long n_items = pairs * (g.n14 + g.n13);
     if (n_items <= 0 || n_items > (1ll << 30)) return (int)cudaErrorInvalidValue;
     g.n_items = (int)n_items;
     g.n_heavy = (int)(pairs * g.n14);
     static const int stagger_env = getenv("DSPB_FIR_STAGGER") ? atoi(getenv("DSPB_FIR_STAGGER")) : 12000;
     g.stagger = stagger_env;
-    g.work = reinterpret_cast<unsigned*>(fp.fft_work);
     g.scratch = reinterpret_cast<float4*>(reinterpret_cast<char*>(fp.fft_work) + kWorkHeader);
     const int grid = (int)std::min<long long>(n_items, std::min(kMaxCtas, 3 * g_tab.n_sm));
     fir_fft_kernel<<<grid, kNT, smem, st>>>(g);
@@ -1017,6 +1294,7 @@ int fir_prepare_spectrum(int log2F, const double* taps_rev_dev, int n_taps, floa
     fir_spectrum_packed_kernel<<<kH2 / 128, 128, 0, st>>>(taps_rev_dev, n_taps, reinterpret_cast<float4*>(H_dev + kF));
     fir_spectrum_kernel<<<1, kNT, smem, st>>>(taps_rev_dev, n_taps, g_tab.Wd, H_dev + 2 * kF, 0, 0.5 / kF);
     fir_spectrum_kernel<<<1, kNT, smem, st>>>(taps_rev_dev, n_taps, g_tab.Wd, H_dev + 3 * kF, 1, 0.5 / kF);
+    fir_spectrum_wide_kernel<<<kN2 / 128, 128, 0, st>>>(taps_rev_dev, n_taps, H_dev + 4 * kF);
     return (int)cudaGetLastError();
 }
 
