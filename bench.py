@@ -50,7 +50,8 @@ def parse_args():
     ap.add_argument("--channels", type=int, default=0,
                     help="strong: TOTAL channels over all GPUs; weak: channels per GPU (default: the workload's)")
     ap.add_argument("--block", type=int, default=1024, help="device block (samples)")
-    ap.add_argument("--blocks-per-step", type=int, default=16)
+    ap.add_argument("--blocks-per-step", type=int, default=24,
+                    help="device blocks per call; 24 x 1024 = 24576 samples = two 12288-sample FIR segments (one 16384-point window each)")
     ap.add_argument("--fir-mode", type=int, default=0)
     ap.add_argument("--iir-mode", type=int, default=0, help="1 = opt-in time-parallel recurrences where the measured error allows (not bit-exact)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")

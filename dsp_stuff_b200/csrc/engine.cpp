@@ -1448,7 +1448,7 @@ int dspb_process(dspb_engine* e, const float* const* inputs, float* const* outpu
     std::vector<float*> dout(n_out);
     for (size_t i = 0; i < n_in; i++) din[i] = e->h_in[i]->p;
     for (size_t i = 0; i < n_out; i++) dout[i] = e->h_out[i]->p;
-    static const int host_chunks = getenv("DSPB_HOST_CHUNKS") ? std::max(1, std::min(64, atoi(getenv("DSPB_HOST_CHUNKS")))) : 8;
+    static const int host_chunks = getenv("DSPB_HOST_CHUNKS") ? std::max(1, std::min(64, atoi(getenv("DSPB_HOST_CHUNKS")))) : 16;
     int n_chunks = host_chunks;
     int per = (C + n_chunks - 1) / n_chunks;
     per = (per + 31) / 32 * 32;  // keep CTA channel groups intact
