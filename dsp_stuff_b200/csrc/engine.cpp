@@ -201,6 +201,16 @@ struct dspb_engine {
     struct ProfRec { int step; cudaEvent_t a, b; };
     std::vector<ProfRec> prof;
     bool plan_only = false;
+    // playback-side sample-rate converter (dspb_resample_dup_stereo): dasp Converter state shared by all channels + the
+    // last 16 pushed frames of every channel
+    struct Resampler {
+        double target_hz = 0.0, value = 0.0;   // Converter::interpolation_value
+        int idx = 0;                           // Sinc::idx (saturates at depth = 8)
+        int cur = 0;
+        DevBuf hist[2];                        // [C x 16] f32, double-buffered
+        DevBuf meta, w;                        // per-call plan on the device
+        size_t cap = 0;
+    } rs;
 
     int find(int64_t id) const {
         for (size_t i = 0; i < nodes.size(); i++)
@@ -1368,6 +1378,7 @@ int dspb_reset_state(dspb_engine* e) {
         int r = clear_node_state(e, *n);
         if (r) return r;
     }
+    e->rs.target_hz = 0.0;  // the next dspb_resample_dup_stereo call builds a fresh converter
     return DSPB_OK;
 }
 
@@ -1505,6 +1516,92 @@ static int boundary_step(dspb_engine* e, const float* src, float* dst, int64_t n
     CUDA_TRY(cudaStreamSynchronize(st));
     return DSPB_OK;
 }
+// ---- 48 kHz -> device-rate converter + duplicate (devices.rs:443-500, 550-556; dasp Converter + Sinc<[f32; 16]>) -------------
+int dspb_resample_dup_stereo(dspb_engine* e, const float* mono, float* interleaved, int64_t n_in, int64_t n_out, double target_hz,
+                             int mem_kind, void* cuda_stream, int64_t* consumed) {
+    if (!e || (n_in > 0 && !mono) || (n_out > 0 && !interleaved)) return fail(DSPB_ERR_INVALID, "null argument");
+    if (n_in < 0 || n_out < 0 || !(target_hz > 0.0)) return fail(DSPB_ERR_INVALID, "n_in, n_out must be >= 0 and target_hz > 0");
+    if (n_out > (1ll << 30) || n_in > (1ll << 30)) return fail(DSPB_ERR_INVALID, "call too long");
+    if (e->plan_only) return fail(DSPB_ERR_CUDA, "engine was created with device = -1 (planning only): no CUDA device, no CPU fallback");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    auto& rs = e->rs;
+    const int C = e->cfg.channels;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (!rs.hist[0].p || rs.target_hz != target_hz) {  // a fresh Converter: value 0, ring of zeros, idx 0 (devices.rs:550-556)
+        for (auto& h : rs.hist) {
+            int r = h.alloc((size_t)C * 16 * 4, true, false);
+            if (r) return r;
+        }
+        rs.target_hz = target_hz;
+        rs.value = 0.0;
+        rs.idx = 0;
+        rs.cur = 0;
+    }
+    // Converter::next control flow, once for all channels (f64, the arithmetic of dasp_signal 0.11.0 interpolate.rs)
+    const double ratio = (double)e->cfg.sample_rate / target_hz;  // from_hz_to_hz: source_hz / target_hz
+    std::vector<int32_t> meta((size_t)n_out * 2);
+    std::vector<double> w((size_t)n_out * 16);
+    int64_t pushed = 0;
+    double value = rs.value;
+    int idx = rs.idx;
+    for (int64_t m = 0; m < n_out; m++) {
+        while (value >= 1.0) {
+            pushed++;
+            if (idx < 8) idx++;
+            value -= 1.0;
+        }
+        meta[2 * m] = (int32_t)pushed;
+        meta[2 * m + 1] = idx;
+        const double phil = value, phir = 1.0 - value;
+        for (int n = 0; n < 8; n++) {  // Sinc::interpolate's window: sinc(a) * (0.5 + 0.5 cos(a / depth)), depth = 8
+            double a = M_PI * (phil + (double)n);
+            w[16 * m + 2 * n] = (a == 0.0 ? 1.0 : std::sin(a) / a) * (0.5 + 0.5 * std::cos(a / 8.0));
+            a = M_PI * (phir + (double)n);
+            w[16 * m + 2 * n + 1] = (a == 0.0 ? 1.0 : std::sin(a) / a) * (0.5 + 0.5 * std::cos(a / 8.0));
+        }
+        value += ratio;
+    }
+    if (pushed > (1ll << 30)) return fail(DSPB_ERR_INVALID, "call too long");
+    if ((size_t)n_out > rs.cap) {
+        int r = rs.meta.alloc((size_t)n_out * 8, false, false);
+        if (r) return r;
+        r = rs.w.alloc((size_t)n_out * 128, false, false);
+        if (r) return r;
+        rs.cap = (size_t)n_out;
+    }
+    const float* din = mono;
+    float* dout = interleaved;
+    float *tin = nullptr, *tout = nullptr;
+    if (mem_kind == DSPB_MEM_HOST) {
+        if (n_in) CUDA_TRY(cudaMallocAsync(&tin, (size_t)C * n_in * 4, st));
+        if (n_out) CUDA_TRY(cudaMallocAsync(&tout, (size_t)C * n_out * 8, st));
+        if (n_in) CUDA_TRY(cudaMemcpyAsync(tin, mono, (size_t)C * n_in * 4, cudaMemcpyHostToDevice, st));
+        din = tin;
+        dout = tout;
+    } else if (mem_kind != DSPB_MEM_DEVICE) {
+        return fail(DSPB_ERR_INVALID, "mem_kind must be DSPB_MEM_DEVICE or DSPB_MEM_HOST");
+    }
+    if (n_out) {
+        // the plan arrays are pageable: these copies return once the data is staged, so the vectors may die with this call
+        CUDA_TRY(cudaMemcpyAsync(rs.meta.p, meta.data(), (size_t)n_out * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(rs.w.p, w.data(), (size_t)n_out * 128, cudaMemcpyHostToDevice, st));
+    }
+    int rc = dspb::launch_resample_dup(din, n_in, rs.hist[rs.cur].p, rs.hist[rs.cur ^ 1].p, rs.meta.p, reinterpret_cast<const double*>(rs.w.p),
+                                       dout, n_out, pushed, C, st);
+    if (rc) return fail(DSPB_ERR_CUDA, "resampler kernel launch: %s", cudaGetErrorString((cudaError_t)rc));
+    if (mem_kind == DSPB_MEM_HOST) {
+        if (n_out) CUDA_TRY(cudaMemcpyAsync(interleaved, tout, (size_t)C * n_out * 8, cudaMemcpyDeviceToHost, st));
+        if (tin) CUDA_TRY(cudaFreeAsync(tin, st));
+        if (tout) CUDA_TRY(cudaFreeAsync(tout, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    rs.cur ^= 1;
+    rs.value = value;
+    rs.idx = idx;
+    if (consumed) *consumed = std::min<int64_t>(pushed, n_in);  // CountingSignal::index stops at the end of its buffer
+    return DSPB_OK;
+}
+
 int dspb_fold_stereo(dspb_engine* e, const float* interleaved, float* mono, int64_t n_frames, int mem_kind, void* cuda_stream) {
     return boundary_step(e, interleaved, mono, n_frames, mem_kind, cuda_stream, true);
 }

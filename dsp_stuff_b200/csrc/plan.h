@@ -184,6 +184,10 @@ size_t fir_fft_work_bytes();       // one launch lane's work area (work counter 
 // device-boundary format steps (boundary.cu): stereo fold a + b, mono -> stereo duplicate; flat [C * n] streams
 int launch_fold_stereo(const float* interleaved, float* mono, long long total_mono, cudaStream_t st);
 int launch_dup_stereo(const float* mono, float* interleaved, long long total_mono, cudaStream_t st);
+// 48 kHz -> device-rate sinc converter + duplicate (boundary.cu): meta = int2 per output frame {frames pushed so far in this
+// call, Sinc::idx}, w = 16 f64 window weights per output frame (left tap n, right tap n interleaved)
+int launch_resample_dup(const float* mono, long long n_in, const float* hist_old, float* hist_new, const void* meta, const double* w,
+                        float* interleaved, long long n_out, long long pushed, int channels, cudaStream_t st);
 // Toeplitz tensor-core path (fir_toeplitz.cu): buffer sizes, tile construction for one tap set
 int fir_toeplitz_max_taps();
 size_t fir_toeplitz_tiles_bytes(int n_taps);

@@ -54,7 +54,7 @@ ABI_SYMBOLS = [
     "dspb_node_set_f32", "dspb_node_set_enum", "dspb_node_set_taps", "dspb_node_set_impulse_response", "dspb_link",
     "dspb_load_graph_json", "dspb_compile", "dspb_process", "dspb_node_process", "dspb_reset_state",
     "dspb_node_get_i64", "dspb_node_port_index", "dspb_describe_plan", "dspb_profile_enable", "dspb_profile_read",
-    "dspb_fold_stereo", "dspb_dup_stereo",
+    "dspb_fold_stereo", "dspb_dup_stereo", "dspb_resample_dup_stereo",
 ]
 
 _lib = None
@@ -92,6 +92,7 @@ def load_library(path: Optional[str] = None):
     L.dspb_describe_plan.argtypes = [vp, vp, i64]
     L.dspb_fold_stereo.argtypes = [vp, vp, vp, i64, ctypes.c_int, vp]
     L.dspb_dup_stereo.argtypes = [vp, vp, vp, i64, ctypes.c_int, vp]
+    L.dspb_resample_dup_stereo.argtypes = [vp, vp, vp, i64, i64, ctypes.c_double, ctypes.c_int, vp, ctypes.POINTER(i64)]
     L.dspb_describe_plan.restype = i64
     if path is None:
         _lib = L
@@ -261,6 +262,17 @@ class Engine:
         out = np.empty(x.shape + (2,), dtype=np.float32)
         self._ck(self._L.dspb_dup_stereo(self._h, x.ctypes.data, out.ctypes.data, x.shape[1], MEM_HOST, None))
         return out
+
+    def resample_dup_stereo(self, mono: np.ndarray, n_out: int, target_hz: float):
+        """[C, n_in] mono at the engine rate -> ([C, n_out, 2] interleaved stereo at target_hz, consumed input samples):
+        the playback callback's sinc converter + duplicate (devices.rs:443-500, 550-556); state carries across calls."""
+        x = np.ascontiguousarray(mono, dtype=np.float32)
+        assert x.ndim == 2 and x.shape[0] == self.channels
+        out = np.empty((self.channels, n_out, 2), dtype=np.float32)
+        used = ctypes.c_int64()
+        self._ck(self._L.dspb_resample_dup_stereo(self._h, x.ctypes.data, out.ctypes.data, x.shape[1], n_out, float(target_hz),
+                                                  MEM_HOST, None, ctypes.byref(used)))
+        return out, used.value
 
     def process(self, inputs, n_samples: Optional[int] = None) -> List[np.ndarray]:
         """Convenience for tests: numpy in, numpy out, through the host-buffer path."""

@@ -161,9 +161,19 @@ int dspb_node_process(dspb_engine* e, int64_t node_id, const float* const* port_
  * [C x n_frames x 2] -> mono [C x n_frames], out = a + b (f32 add, not an average).  Any n_frames >= 0. */
 int dspb_fold_stereo(dspb_engine* e, const float* interleaved, float* mono, int64_t n_frames, int mem_kind, void* cuda_stream);
 /* Replaces: the mono -> stereo duplicate of the playback callback, devices.rs:443-500 `do_write_2`
- * (`o.fill(x)`): mono [C x n_frames] -> interleaved [C x n_frames x 2].  The 48 kHz -> device-rate sinc resampler
- * in front of it (dasp Sinc<[f32;16]>, un-vendored) is not part of this library: streams stay at 48 kHz. */
+ * (`o.fill(x)`): mono [C x n_frames] -> interleaved [C x n_frames x 2] at the graph's own rate.  With the 48 kHz ->
+ * device-rate converter in front of it: dspb_resample_dup_stereo below. */
 int dspb_dup_stereo(dspb_engine* e, const float* mono, float* interleaved, int64_t n_frames, int mem_kind, void* cuda_stream);
+
+/* Replaces: the playback callback's sample-rate converter + duplicate, devices.rs:443-500 `do_write_2` with the converter
+ * built at devices.rs:550-556: `Converter::from_hz_to_hz(CountingSignal, Sinc::new(Fixed::from([0.0; 16])), 48_000.0, target)`
+ * (dasp_signal 0.11.0 / dasp_interpolate 0.11.0, un-vendored: restated from the published crates, parity UNPINNED).
+ * mono [C x n_in] at the engine's sample rate -> interleaved stereo [C x n_out x 2] at target_hz, both slots of a frame equal.
+ * The converter state (fractional position, the 16-frame sinc ring) carries over to the next call with the same target_hz; a
+ * different target_hz or dspb_reset_state starts a fresh converter.  *consumed (may be NULL) = input samples taken, what
+ * do_write_2 releases from the link ring; input beyond n_in reads as zeros (CountingSignal::next, devices.rs:380-386). */
+int dspb_resample_dup_stereo(dspb_engine* e, const float* mono, float* interleaved, int64_t n_in, int64_t n_out,
+                             double target_hz, int mem_kind, void* cuda_stream, int64_t* consumed);
 
 /* Clears all per-channel state (what a fresh NodeStatic::new / restore gives). */
 int dspb_reset_state(dspb_engine* e);

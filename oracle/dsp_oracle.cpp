@@ -811,4 +811,88 @@ int orc_node_process(void* h, int64_t id, const float* const* port_in, const uin
     return OK;
 }
 
+
+// ---- playback-side sample-rate converter -----------------------------------------------------
+// devices.rs:550-556 builds `Converter::from_hz_to_hz(CountingSignal::new(), Sinc::new(Fixed::from([0.0; 16])), 48_000.0,
+// target)` and devices.rs:443-500 (`do_write_2`) pulls one frame per stereo output frame from it and writes it to both slots.
+// The arithmetic lives in two crates that are NOT under /root/reference (Cargo.lock:1229-1236, 1273-1284): dasp_signal
+// 0.11.0 `interpolate::Converter` and dasp_interpolate 0.11.0 `sinc::Sinc`; restated here from their published sources --
+// PARITY UNPINNED, like biquad / dasp_envelope / rivulet:
+//   Converter::next:   while interpolation_value >= 1.0 { interpolator.next_source_frame(source.next()); value -= 1.0 }
+//                      out = interpolator.interpolate(value); value += source_hz / target_hz
+//   Sinc::next_source_frame: frames.push(frame) (a 16-frame ring, oldest dropped); if idx < depth { idx += 1 }   (depth = 8)
+//   Sinc::interpolate(x):    nl = idx, nr = idx + 1; max_depth = nl + depth >= 16 ? 16 - depth : nr - depth < 0 ? nr : depth;
+//                            v = 0; for n in 0..max_depth { a = PI (x + n);       v += f32(sinc(a) hann(a) f64(frames[nl - n]))
+//                                                           a = PI (1 - x + n);   v += f32(sinc(a) hann(a) f64(frames[nr + n])) }
+//                            sinc(a) = a == 0 ? 1 : sin(a) / a, hann(a) = 0.5 + 0.5 cos(a / depth); ring_buffer::Fixed indexes
+//                            modulo its length, so frames[16] (n = 7 on the right in the steady state) is the OLDEST frame.
+//   CountingSignal::next (devices.rs:377-392): inner[index++] while inside the prepared buffer, 0.0 (index unchanged) beyond.
+struct SincConverter {
+    double value = 0.0, ratio = 1.0;
+    float ring[16];
+    int first = 0, idx = 0;
+    SincConverter() { for (auto& r : ring) r = 0.0f; }
+    float frame(int i) const { return ring[(first + i) % 16]; }
+    void push(float f) { ring[first] = f; first = (first + 1) % 16; if (idx < 8) idx++; }
+    float interpolate(double x) const {
+        const int depth = 8, nl = idx, nr = idx + 1;
+        const int rightmost = nl + depth, leftmost = nr - depth;
+        const int max_depth = rightmost >= 16 ? 16 - depth : (leftmost < 0 ? depth + leftmost : depth);
+        const double phil = x, phir = 1.0 - x;
+        float v = 0.0f;
+        for (int n = 0; n < max_depth; n++) {
+            double a = M_PI * (phil + (double)n);
+            double first_ = a == 0.0 ? 1.0 : std::sin(a) / a;
+            double second = 0.5 + 0.5 * std::cos(a / (double)depth);
+            v = v + (float)(first_ * second * (double)frame(nl - n));
+            a = M_PI * (phir + (double)n);
+            first_ = a == 0.0 ? 1.0 : std::sin(a) / a;
+            second = 0.5 + 0.5 * std::cos(a / (double)depth);
+            v = v + (float)(first_ * second * (double)frame(nr + n));
+        }
+        return v;
+    }
+};
+struct Resampler {
+    int channels;
+    std::vector<SincConverter> conv;
+};
+
+int orc_resampler_create(int channels, double source_hz, double target_hz, void** out) {
+    if (channels <= 0 || !(source_hz > 0.0) || !(target_hz > 0.0) || !out) return fail(E_INVALID, "bad resampler arguments");
+    auto* r = new Resampler{channels, std::vector<SincConverter>((size_t)channels)};
+    for (auto& c : r->conv) c.ratio = source_hz / target_hz;  // Converter::from_hz_to_hz -> scale_playback_hz(source / target)
+    *out = r;
+    return OK;
+}
+void orc_resampler_destroy(void* h) { delete (Resampler*)h; }
+
+// mono [C x n_in] at 48 kHz -> interleaved stereo [C x n_out x 2] at the target rate; *consumed = CountingSignal::index after
+// the call (what do_write_2 releases from the link ring), identical for every channel.
+int orc_resampler_process(void* h, const float* mono, int64_t n_in, float* interleaved, int64_t n_out, int64_t* consumed) {
+    Resampler& r = *(Resampler*)h;
+    int64_t used = 0;
+    for (int ch = 0; ch < r.channels; ch++) {
+        SincConverter& c = r.conv[(size_t)ch];
+        const float* src = mono + (size_t)ch * n_in;
+        float* dst = interleaved + (size_t)ch * n_out * 2;
+        int64_t index = 0;  // CountingSignal::prep resets it
+        for (int64_t m = 0; m < n_out; m++) {
+            while (c.value >= 1.0) {
+                float f = 0.0f;
+                if (index < n_in) f = src[index++];
+                c.push(f);
+                c.value -= 1.0;
+            }
+            const float x = c.interpolate(c.value);
+            c.value += c.ratio;
+            dst[2 * m] = x;      // o.fill(x), devices.rs:487-491
+            dst[2 * m + 1] = x;
+        }
+        used = index;
+    }
+    if (consumed) *consumed = used;
+    return OK;
+}
+
 }  // extern "C"

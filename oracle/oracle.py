@@ -49,6 +49,11 @@ def lib():
         L.orc_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
         L.orc_node_process.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
                                        ctypes.c_void_p, ctypes.c_int64]
+        L.orc_resampler_create.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_void_p)]
+        L.orc_resampler_destroy.argtypes = [ctypes.c_void_p]
+        L.orc_resampler_destroy.restype = None
+        L.orc_resampler_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                            ctypes.POINTER(ctypes.c_int64)]
         _lib = L
     return _lib
 
@@ -148,3 +153,35 @@ class Oracle:
         op = (ctypes.c_void_p * n_outputs)(*[y.ctypes.data for y in outs])
         self._ck(self._L.orc_node_process(self._h, node_id, ip, pres, op, n))
         return outs
+
+
+class Resampler:
+    """Playback-side converter of the reference (devices.rs:443-500, 550-556): 48 kHz mono -> target-rate stereo through
+    dasp's Converter + Sinc<[f32; 16]> (restated from the published crates: parity UNPINNED, see dsp_oracle.cpp)."""
+
+    def __init__(self, channels: int, target_hz: float, source_hz: float = 48000.0):
+        self._L = lib()
+        self.channels = channels
+        h = ctypes.c_void_p()
+        rc = self._L.orc_resampler_create(channels, float(source_hz), float(target_hz), ctypes.byref(h))
+        if rc:
+            raise OracleError(rc, self._L.orc_last_error().decode())
+        self._h = h
+
+    def process(self, mono, n_out: int):
+        """-> (interleaved [C, n_out, 2] float32, consumed input samples)"""
+        x = np.ascontiguousarray(mono, dtype=np.float32)
+        assert x.ndim == 2 and x.shape[0] == self.channels
+        out = np.zeros((self.channels, n_out, 2), dtype=np.float32)
+        used = ctypes.c_int64()
+        rc = self._L.orc_resampler_process(self._h, x.ctypes.data, x.shape[1], out.ctypes.data, n_out, ctypes.byref(used))
+        if rc:
+            raise OracleError(rc, self._L.orc_last_error().decode())
+        return out, used.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.orc_resampler_destroy(self._h)
+            self._h = None
+
+    __del__ = close

@@ -41,3 +41,28 @@ def test_device_pointer_form_at_full_width():
     assert torch.equal(mono, v[:, :, 0] + v[:, :, 1])
     assert torch.equal(back.view(C, n, 2)[:, :, 0], mono) and torch.equal(back.view(C, n, 2)[:, :, 1], mono)
     # the fold composes with the effect path: fold -> engine graph == engine graph on the folded signal (same buffers)
+
+
+@pytest.mark.parametrize("target,C,calls", [(44100.0, 5, [(4800, 4000), (4800, 4000), (300, 200)]), (96000.0, 3, [(2048, 4000), (1024, 2000)]),
+                                            (48000.0, 2, [(512, 500)]), (22050.0, 4, [(4096, 1800), (128, 40)]),
+                                            (44100.0, 2, [(100, 400)])])      # the last: output wants more input than given -> zeros
+def test_resample_dup_matches_the_restated_dasp_converter(oracle_mod, target, C, calls):
+    """dspb_resample_dup_stereo (devices.rs:443-500, 550-556) against the oracle's restatement of dasp's Converter +
+    Sinc<[f32; 16]>: bit for bit (the window weights come from the same libm on the host, the kernel does the reference's
+    f64 multiply -> f32 round -> f32 add in the reference's order), consumed counts equal, state carried across calls."""
+    e = Engine(C, block=128, max_samples=128)
+    r = oracle_mod.Resampler(C, target)
+    x = S.noise(C, sum(n for n, _ in calls) + 16, seed=3)
+    off = 0
+    for n_in, n_out in calls:
+        blk = x[:, off:off + n_in]
+        got, used = e.resample_dup_stereo(blk, n_out, target)
+        ref, used_ref = r.process(blk, n_out)
+        assert used == used_ref
+        assert_bit_exact(got.reshape(C, -1), ref.reshape(C, -1), f"resample to {target} Hz")
+        assert np.array_equal(got[:, :, 0], got[:, :, 1])
+        off += used
+    e.reset_state()   # a fresh converter after reset
+    got, _ = e.resample_dup_stereo(x[:, :256], 200, target)
+    ref, _ = oracle_mod.Resampler(C, target).process(x[:, :256], 200)
+    assert_bit_exact(got.reshape(C, -1), ref.reshape(C, -1), "after reset")

@@ -230,3 +230,31 @@ def test_gate_extension_known_answers(oracle_mod):
     nz = int(np.count_nonzero(y[0]))
     assert abs(nz - open_len) <= 2, (nz, open_len)
     assert np.all(y[0, nz:] == 0.0)
+
+
+# ---- playback-side converter (devices.rs:443-500, 550-556; dasp Converter + Sinc<[f32; 16]>, restated: parity unpinned) ----
+def test_resampler_unity_rate_is_an_eight_frame_delay(oracle_mod):
+    """target = 48 kHz: interpolation_value is 0 at every output, so only the left n = 0 tap has weight 1 (sinc(0)); the right
+    taps sit at multiples of pi (sin ~ 1e-16).  Sinc::idx saturates at depth = 8, i.e. the output is frames[8] of 16: the
+    input delayed by 8 frames -- derived by hand from the restated Sinc::interpolate."""
+    r = oracle_mod.Resampler(2, 48000.0)
+    x = S.noise(2, 256)
+    y, used = r.process(x, 200)
+    assert used == 199                       # the first next() pushes nothing (value starts at 0.0)
+    assert np.array_equal(y[:, :, 0], y[:, :, 1])          # o.fill(x): both slots of a frame
+    assert np.allclose(y[:, 16:, 0], x[:, 8:192], rtol=0, atol=1e-7)
+    assert np.abs(y[:, :8, 0]).max() < 1e-7   # start-up: idx < depth, the unit-weight tap still points at the zero-filled ring
+
+
+def test_resampler_44k1_tracks_a_sine_and_carries_state(oracle_mod):
+    n = 4800
+    x = np.sin(2 * np.pi * 1000.0 * np.arange(2 * n) / 48000.0).astype(np.float32)[None]
+    r = oracle_mod.Resampler(1, 44100.0)
+    y1, u1 = r.process(x[:, :n], 4000)
+    y2, u2 = r.process(x[:, u1:], 4000)      # the caller re-presents what was not consumed (source.release(index))
+    y = np.concatenate([y1, y2], axis=1)[0, :, 0]
+    t = (np.arange(8000) * 48000.0 / 44100.0 - 8.0) / 48000.0
+    assert np.max(np.abs(y[100:] - np.sin(2 * np.pi * 1000.0 * t[100:]))) < 3e-3   # 16-tap Hann-windowed sinc
+    one, _ = oracle_mod.Resampler(1, 44100.0).process(x, 8000)
+    assert np.array_equal(one[0, :, 0], y)   # two calls == one call
+    assert abs(u1 - 4000 * 48000 / 44100) <= 2
