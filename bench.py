@@ -451,8 +451,9 @@ def main():
     barrier()
 
     # ---- end to end through the host-buffer C-ABI call (pinned memory; H2D + kernels + D2H per step) ---------------
-    e2e_ms, h2d_ms, d2h_ms = 0.0, 0.0, 0.0
+    e2e_ms, e2e_sync_ms, h2d_ms, d2h_ms = 0.0, 0.0, 0.0, 0.0
     if not args.no_e2e:
+        # (a) the blocking call, one step at a time
         for _ in range(2):
             eng.process_host(x_host, y_host, n)
         barrier()
@@ -460,6 +461,20 @@ def main():
         for _ in range(args.steps):
             eng.process_host(x_host, y_host, n)
         torch.cuda.synchronize()
+        e2e_sync_ms = (time.perf_counter() - t0) * 1e3
+        # (b) the streaming form of the same call (DSPB_MEM_HOST_ASYNC + dspb_sync): two sets of pinned buffers, step k+1's
+        # H2D runs next to step k's D2H; every step still copies its inputs in and its results out inside the timed region
+        x_host2 = [t.clone().pin_memory() for t in x_host]
+        y_host2 = [torch.empty_like(t).pin_memory() for t in y_host]
+        sets = [(x_host, y_host), (x_host2, y_host2)]
+        for k in range(2):
+            eng.process_host(*sets[k % 2], n, wait=False)
+        eng.sync()
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            eng.process_host(*sets[k % 2], n, wait=False)
+        eng.sync()
         e2e_ms = (time.perf_counter() - t0) * 1e3
         # the two copy directions alone, all ranks at once: what the host side (PCIe + host memory) gives this job
         reps = 5
@@ -526,7 +541,7 @@ def main():
         weak = {"value": float(world) * C * n * args.steps / (wms * 1e-3), "unit": UNIT, "channels_per_gpu": C,
                 "ms_per_step": wms / args.steps, "scaling": "weak"}
 
-    e2e_ms, gather_ms, h2d_ms, d2h_ms = allmax([e2e_ms, gather_ms or 0.0, h2d_ms, d2h_ms])
+    e2e_ms, e2e_sync_ms, gather_ms, h2d_ms, d2h_ms = allmax([e2e_ms, e2e_sync_ms, gather_ms or 0.0, h2d_ms, d2h_ms])
 
     if rank == 0:
         total = float(C_total) * n * args.steps
@@ -588,6 +603,9 @@ def main():
             bi, bo = n_in * C_local * n * 4, n_out * C_local * n * 4
             line["e2e"] = {"value": float(C_total) * n * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
                            "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo, "ms_per_step": e2e_ms / args.steps,
+                           "api": "dspb_process(DSPB_MEM_HOST_ASYNC) per step on alternating pinned buffer sets + dspb_sync",
+                           "blocking_call": {"value": float(C_total) * n * args.steps / (e2e_sync_ms * 1e-3), "unit": UNIT,
+                                             "ms_per_step": e2e_sync_ms / args.steps, "api": "dspb_process(DSPB_MEM_HOST), returns when the outputs are complete"},
                            "copies_alone": {"h2d_ms": h2d_ms, "d2h_ms": d2h_ms,
                                             "h2d_gbs_per_gpu": bi / (h2d_ms * 1e-3) / 1e9 if h2d_ms else None,
                                             "d2h_gbs_per_gpu": bo / (d2h_ms * 1e-3) / 1e9 if d2h_ms else None,

@@ -201,6 +201,8 @@ struct dspb_engine {
     struct ProfRec { int step; cudaEvent_t a, b; };
     std::vector<ProfRec> prof;
     bool plan_only = false;
+    bool host_inflight = false;   // a DSPB_MEM_HOST_ASYNC call may still be running on the internal streams
+    int64_t host_last_n = 0;
     // playback-side sample-rate converter (dspb_resample_dup_stereo): dasp Converter state shared by all channels + the
     // last 16 pushed frames of every channel
     struct Resampler {
@@ -1216,6 +1218,15 @@ int check_ready(dspb_engine* e, int64_t n) {
 extern "C" {
 
 const char* dspb_last_error(void) { return g_err.c_str(); }
+int dspb_sync(dspb_engine* e);
+// parameter / structure changes touch state the asynchronous host calls still use: finish those first
+#define DSPB_QUIESCE(e)                                   \
+    do {                                                  \
+        if ((e)->host_inflight) {                         \
+            int _q = dspb_sync(e);                        \
+            if (_q) return _q;                            \
+        }                                                 \
+    } while (0)
 int dspb_abi_version(void) { return DSPB_ABI_VERSION; }
 
 int dspb_engine_create(const dspb_config* cfg, dspb_engine** out) {
@@ -1294,6 +1305,7 @@ int dspb_node_set_f32(dspb_engine* e, int64_t node_id, const char* field, float 
     Node& n = *e->nodes[i];
     int p = param_index(kNodeTypes[n.type], field);
     if (p < 0) return fail(DSPB_ERR_UNKNOWN_PORT, "node type '%s' has no f32 field '%s'", kNodeTypes[n.type].cfg_name, field);
+    DSPB_QUIESCE(e);
     n.f32[p] = value;
     if (!e->plan_only) CUDA_TRY(cudaSetDevice(e->cfg.device));
     if (n.type == T_BIQUAD) {  // after_settings_change = regenerate_filter: new coefficients + reset_state
@@ -1318,6 +1330,7 @@ int dspb_node_set_enum(dspb_engine* e, int64_t node_id, const char* field, const
         if (!strcmp(nt.enums[k].name, field)) {
             for (size_t v = 0; v < nt.enums[k].variants.size(); v++)
                 if (!strcmp(nt.enums[k].variants[v], variant)) {
+                    DSPB_QUIESCE(e);
                     n.enums[k] = (int)v;
                     e->lowered = false;
                     return DSPB_OK;
@@ -1333,6 +1346,7 @@ int dspb_node_set_taps(dspb_engine* e, int64_t node_id, const double* taps, int6
     if (i < 0) return fail(DSPB_ERR_UNKNOWN_NODE, "unknown node id %lld", (long long)node_id);
     Node& n = *e->nodes[i];
     if (n.type != T_FIR) return fail(DSPB_ERR_INVALID, "node %lld is not a fir", (long long)node_id);
+    DSPB_QUIESCE(e);
     n.taps.assign(taps, taps + n_taps);
     n.fir_dirty = true;
     e->lowered = false;
@@ -1361,6 +1375,7 @@ int dspb_link(dspb_engine* e, int64_t src_node, const char* out_port, int64_t ds
 
 int dspb_compile(dspb_engine* e) {
     if (!e) return fail(DSPB_ERR_INVALID, "null engine");
+    DSPB_QUIESCE(e);
     if (!e->plan_only) CUDA_TRY(cudaSetDevice(e->cfg.device));
     int r = topo_sort(e);
     if (r) return r;
@@ -1374,6 +1389,7 @@ int dspb_reset_state(dspb_engine* e) {
     if (e->plan_only) return fail(DSPB_ERR_CUDA, "planning-only engine (device -1) holds no state");
     CUDA_TRY(cudaSetDevice(e->cfg.device));
     CUDA_TRY(cudaDeviceSynchronize());
+    e->host_inflight = false;
     for (auto& n : e->nodes) {
         int r = clear_node_state(e, *n);
         if (r) return r;
@@ -1396,6 +1412,10 @@ int dspb_process(dspb_engine* e, const float* const* inputs, float* const* outpu
     for (size_t i = 0; i < n_out; i++)
         if (!outputs[i]) return fail(DSPB_ERR_INVALID, "null output buffer %zu", i);
     e->last_launches = 0;
+    if (mem_kind == DSPB_MEM_DEVICE && e->host_inflight) {  // state is shared: finish the asynchronous host calls first
+        int rs = dspb_sync(e);
+        if (rs) return rs;
+    }
     if (mem_kind == DSPB_MEM_DEVICE) {
         for (size_t i = 0; i < n_in; i++)
             if ((uintptr_t)inputs[i] & 15) return fail(DSPB_ERR_INVALID, "device buffers must be 16-byte aligned");
@@ -1435,9 +1455,17 @@ int dspb_process(dspb_engine* e, const float* const* inputs, float* const* outpu
         advance_state(e, n);
         return DSPB_OK;
     }
-    if (mem_kind != DSPB_MEM_HOST) return fail(DSPB_ERR_INVALID, "mem_kind must be DSPB_MEM_DEVICE or DSPB_MEM_HOST");
+    if (mem_kind != DSPB_MEM_HOST && mem_kind != DSPB_MEM_HOST_ASYNC)
+        return fail(DSPB_ERR_INVALID, "mem_kind must be DSPB_MEM_DEVICE, DSPB_MEM_HOST or DSPB_MEM_HOST_ASYNC");
     // Host buffers: channel ranges are independent, so H2D / kernels / D2H of successive channel
-    // chunks overlap on three streams.
+    // chunks overlap on three streams.  DSPB_MEM_HOST_ASYNC returns without waiting: the next call's H2D then runs next
+    // to this call's D2H (PCIe is full duplex); chunk k of a call waits for chunk k of the previous one wherever the two
+    // share a staging region (events below), which needs the same n and chunking -- otherwise the calls are serialised.
+    if (e->host_inflight && (e->host_last_n != n)) {
+        CUDA_TRY(cudaStreamSynchronize(e->s_d2h));
+        CUDA_TRY(cudaStreamSynchronize(e->s_cmp));
+        e->host_inflight = false;
+    }
     if (!e->s_cmp) {
         CUDA_TRY(cudaStreamCreateWithFlags(&e->s_h2d, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&e->s_cmp, cudaStreamNonBlocking));
@@ -1464,27 +1492,50 @@ int dspb_process(dspb_engine* e, const float* const* inputs, float* const* outpu
     int per = (C + n_chunks - 1) / n_chunks;
     per = (per + 31) / 32 * 32;  // keep CTA channel groups intact
     n_chunks = (C + per - 1) / per;
-    while ((int)e->ev_pool.size() < 2 * n_chunks) {
+    while ((int)e->ev_pool.size() < 3 * n_chunks) {
         cudaEvent_t ev;
         CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         e->ev_pool.push_back(ev);
     }
     for (int k = 0; k < n_chunks; k++) {
         const int c0 = k * per, c1 = std::min(C, c0 + per);
+        cudaEvent_t ev_h2d = e->ev_pool[3 * k], ev_cmp = e->ev_pool[3 * k + 1], ev_d2h = e->ev_pool[3 * k + 2];
+        // the previous (asynchronous) call's kernels of this chunk still read the staging region this copy overwrites
+        if (e->host_inflight) CUDA_TRY(cudaStreamWaitEvent(e->s_h2d, ev_cmp, 0));
         for (size_t i = 0; i < n_in; i++)
             CUDA_TRY(cudaMemcpyAsync(e->h_in[i]->p + (size_t)c0 * n, inputs[i] + (size_t)c0 * n, (size_t)(c1 - c0) * n * 4, cudaMemcpyHostToDevice, e->s_h2d));
-        CUDA_TRY(cudaEventRecord(e->ev_pool[2 * k], e->s_h2d));
-        CUDA_TRY(cudaStreamWaitEvent(e->s_cmp, e->ev_pool[2 * k], 0));
+        CUDA_TRY(cudaEventRecord(ev_h2d, e->s_h2d));
+        CUDA_TRY(cudaStreamWaitEvent(e->s_cmp, ev_h2d, 0));
+        // ... and its D2H of this chunk still reads the output staging region these kernels overwrite
+        if (e->host_inflight) CUDA_TRY(cudaStreamWaitEvent(e->s_cmp, ev_d2h, 0));
         r = run_steps(e, din.data(), dout.data(), n, c0, c1, e->s_cmp);
         if (r) return r;
-        CUDA_TRY(cudaEventRecord(e->ev_pool[2 * k + 1], e->s_cmp));
-        CUDA_TRY(cudaStreamWaitEvent(e->s_d2h, e->ev_pool[2 * k + 1], 0));
+        CUDA_TRY(cudaEventRecord(ev_cmp, e->s_cmp));
+        CUDA_TRY(cudaStreamWaitEvent(e->s_d2h, ev_cmp, 0));
         for (size_t i = 0; i < n_out; i++)
             CUDA_TRY(cudaMemcpyAsync(outputs[i] + (size_t)c0 * n, e->h_out[i]->p + (size_t)c0 * n, (size_t)(c1 - c0) * n * 4, cudaMemcpyDeviceToHost, e->s_d2h));
+        CUDA_TRY(cudaEventRecord(ev_d2h, e->s_d2h));
+    }
+    advance_state(e, n);
+    e->host_last_n = n;
+    if (mem_kind == DSPB_MEM_HOST_ASYNC) {
+        e->host_inflight = true;
+        return DSPB_OK;
     }
     CUDA_TRY(cudaStreamSynchronize(e->s_d2h));
     CUDA_TRY(cudaStreamSynchronize(e->s_cmp));
-    advance_state(e, n);
+    e->host_inflight = false;
+    return DSPB_OK;
+}
+
+int dspb_sync(dspb_engine* e) {
+    if (!e) return fail(DSPB_ERR_INVALID, "null engine");
+    if (e->plan_only) return DSPB_OK;
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    if (e->s_d2h) CUDA_TRY(cudaStreamSynchronize(e->s_d2h));
+    if (e->s_cmp) CUDA_TRY(cudaStreamSynchronize(e->s_cmp));
+    if (e->s_h2d) CUDA_TRY(cudaStreamSynchronize(e->s_h2d));
+    e->host_inflight = false;
     return DSPB_OK;
 }
 

@@ -21,6 +21,7 @@ _LIB_PATH = os.path.join(_HERE, "libdspb200.so")
 
 MEM_DEVICE = 0
 MEM_HOST = 1
+MEM_HOST_ASYNC = 2
 FIR_FFT = 0
 FIR_DIRECT = 1
 FIR_TOEPLITZ = 2
@@ -54,7 +55,7 @@ ABI_SYMBOLS = [
     "dspb_node_set_f32", "dspb_node_set_enum", "dspb_node_set_taps", "dspb_node_set_impulse_response", "dspb_link",
     "dspb_load_graph_json", "dspb_compile", "dspb_process", "dspb_node_process", "dspb_reset_state",
     "dspb_node_get_i64", "dspb_node_port_index", "dspb_describe_plan", "dspb_profile_enable", "dspb_profile_read",
-    "dspb_fold_stereo", "dspb_dup_stereo", "dspb_resample_dup_stereo",
+    "dspb_fold_stereo", "dspb_dup_stereo", "dspb_resample_dup_stereo", "dspb_sync",
 ]
 
 _lib = None
@@ -93,6 +94,7 @@ def load_library(path: Optional[str] = None):
     L.dspb_fold_stereo.argtypes = [vp, vp, vp, i64, ctypes.c_int, vp]
     L.dspb_dup_stereo.argtypes = [vp, vp, vp, i64, ctypes.c_int, vp]
     L.dspb_resample_dup_stereo.argtypes = [vp, vp, vp, i64, i64, ctypes.c_double, ctypes.c_int, vp, ctypes.POINTER(i64)]
+    L.dspb_sync.argtypes = [vp]
     L.dspb_describe_plan.restype = i64
     if path is None:
         _lib = L
@@ -230,9 +232,14 @@ class Engine:
         op = (ctypes.c_void_p * max(1, len(outputs)))(*[t.data_ptr() for t in outputs])
         self._ck(self._L.dspb_process(self._h, ip, op, n_samples, MEM_DEVICE, ctypes.c_void_p(st.cuda_stream)))
 
-    def process_host(self, inputs: Sequence, outputs: Sequence, n_samples: int):
+    def sync(self):
+        """Waits for every process_host(..., wait=False) call."""
+        self._ck(self._L.dspb_sync(self._h))
+
+    def process_host(self, inputs: Sequence, outputs: Sequence, n_samples: int, wait: bool = True):
         """inputs/outputs: host float32 buffers [C, n] (numpy arrays or CPU torch tensors, pinned for
-        full speed).  Copies in, runs and copies out (pipelined over channel chunks); blocks until done."""
+        full speed).  Copies in, runs and copies out (pipelined over channel chunks); blocks until done unless
+        wait=False (DSPB_MEM_HOST_ASYNC: keep the buffers alive and untouched until sync())."""
         assert len(inputs) == self._n_in and len(outputs) == self._n_out
 
         def ptr(a):
@@ -244,7 +251,7 @@ class Engine:
 
         ip = (ctypes.c_void_p * max(1, len(inputs)))(*[ptr(t) for t in inputs])
         op = (ctypes.c_void_p * max(1, len(outputs)))(*[ptr(t) for t in outputs])
-        self._ck(self._L.dspb_process(self._h, ip, op, n_samples, MEM_HOST, None))
+        self._ck(self._L.dspb_process(self._h, ip, op, n_samples, MEM_HOST if wait else MEM_HOST_ASYNC, None))
 
     # ---- device-boundary format steps (devices.rs:244-262, 443-500) ---------------------------------------
     def fold_stereo(self, interleaved: np.ndarray) -> np.ndarray:

@@ -45,6 +45,11 @@ typedef enum dspb_status {
 #define DSPB_MEM_HOST 1   /* host pointers (pinned for full speed); H2D, kernels and D2H are pipelined
                              inside the call, which returns after the outputs are complete */
 
+#define DSPB_MEM_HOST_ASYNC 2 /* like DSPB_MEM_HOST, but the call returns as soon as the work is enqueued on the engine's
+                                own streams: the next call's H2D overlaps this call's D2H.  The caller keeps both host
+                                buffers untouched (pinned memory, or the copies degrade to synchronous ones) until
+                                dspb_sync returns, and passes DIFFERENT buffers to calls that may be in flight together. */
+
 typedef struct dspb_engine dspb_engine;
 
 /* Engine configuration.  Constants the reference hard-codes are fields here so
@@ -146,6 +151,9 @@ int dspb_compile(dspb_engine* e);
  * State (IIR, rings, FIR history, clocks) carries over to the next call. */
 int dspb_process(dspb_engine* e, const float* const* inputs, float* const* outputs, int64_t n_samples,
                  int mem_kind, void* cuda_stream);
+
+/* Waits for every DSPB_MEM_HOST_ASYNC call issued on this engine (outputs complete, input buffers free again). */
+int dspb_sync(dspb_engine* e);
 
 /* Replaces: one call of SimpleNode::process(ProcessInput, ProcessOutput) (node.rs:135-146) on one
  * node, batched over channels: inputs are taken as ALREADY averaged port buffers with their

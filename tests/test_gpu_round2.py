@@ -213,3 +213,35 @@ def test_planning_engine_next_to_a_real_engine(oracle_mod):
     spec.apply(live)                           # ... and must not poison this one
     assert "fused segment" in plan.describe_plan()
     assert_bit_exact(live.process(x)[0], make_oracle(oracle_mod, spec, 4).process(x)[0], "live engine next to a planning engine")
+
+
+def test_async_host_calls_equal_blocking_calls(oracle_mod):
+    """DSPB_MEM_HOST_ASYNC + dspb_sync: several calls in flight on alternating buffers give exactly what the blocking call
+    gives (staging regions are protected chunk by chunk across calls), setters in between quiesce the engine first."""
+    import torch
+
+    spec = S.target_chain(300)
+    C, n, calls = 96, 128 * 24, 5
+    x = S.noise(C, n * calls)
+    a = make_engine(spec, C, n, fir_mode=FIR_FFT)
+    ref = np.concatenate([a.process(x[:, k * n:(k + 1) * n])[0] for k in range(calls)], axis=1)
+    b = make_engine(spec, C, n, fir_mode=FIR_FFT)
+    xin = [torch.from_numpy(np.ascontiguousarray(x[:, k * n:(k + 1) * n])).pin_memory() for k in range(calls)]
+    out = [torch.empty((C, n), dtype=torch.float32).pin_memory() for _ in range(calls)]
+    for k in range(calls):
+        b.process_host([xin[k]], [out[k]], n, wait=False)
+    b.sync()
+    got = np.concatenate([o.numpy() for o in out], axis=1)
+    assert_bit_exact(got, ref, "async == blocking")
+    # a setter while calls are in flight: applied after them, like the blocking sequence
+    for e in (a, b):
+        e.reset_state()
+    ya = [a.process(x[:, :n])[0]]
+    a.set_f32(0, "level", 0.5)
+    ya.append(a.process(x[:, n:2 * n])[0])
+    b.process_host([xin[0]], [out[0]], n, wait=False)
+    b.set_f32(0, "level", 0.5)
+    b.process_host([xin[1]], [out[1]], n, wait=False)
+    b.sync()
+    assert_bit_exact(out[0].numpy(), ya[0], "before the setter")
+    assert_bit_exact(out[1].numpy(), ya[1], "after the setter")
