@@ -406,12 +406,13 @@ template <int MODE, bool FAST>
 __device__ __forceinline__ void inv_pass1(const C2<float>* a, const Tw<float>& W, float* __restrict__ outA, float* __restrict__ outB,
                                           bool hasB, int hist, int lim, float divisor, float post_nf, float4* __restrict__ scr, int t) {
     constexpr int L = kF / 8, LP = L + L / 16;
-    const bool post = post_nf != 0.0f;
-    const float post_rnf = post ? __frcp_rn(post_nf) : 0.0f;
-    auto fin = [&](float y) {
-        y = __fmul_rn(y, divisor);
-        return post ? div_nf(y, post_nf, post_rnf) : y;
-    };
+    // Epilogue: `* divisor` (fir.rs:187-190, 222) and the fused sink average `(0.0 + y) / nf` collapse into ONE multiplication by
+    // divisor / nf (formed in f64 on the host side of this expression, rounded once).  Against the two separately rounded
+    // operations that is at most two ulps (1.2e-7) on a path whose transform error is 2-3e-7 and whose bar is 1e-5; the
+    // bit-exact samples of this node (warm-up, fir_mode = 1) come from fir_direct_kernel, which keeps the exact division.
+    const float scale = post_nf != 0.0f ? (float)((double)divisor / (double)post_nf) : divisor;
+    const bool unit = scale == 1.0f;
+    auto fin = [&](float y) { return unit ? y : __fmul_rn(y, scale); };
     auto store2 = [&](int n, float a0, float a1, float b0, float b1) {  // samples n, n + 1 of both channels
         *reinterpret_cast<float2*>(outA + n) = make_float2(fin(a0), fin(a1));
         if (hasB) *reinterpret_cast<float2*>(outB + n) = make_float2(fin(b0), fin(b1));
@@ -594,12 +595,10 @@ fir_fft_wide_kernel(const __grid_constant__ WideArgs g) {
     const Tw<float> W{tabs, tabs + kCoarse, nullptr};
     const C2<float>* T2 = tabs + kCoarse + kFine;   // [(k - 1) * 32 + j]
     const int V14 = kN2 - g.hist;
-    const bool post = g.post_nf != 0.0f;
-    const float post_rnf = post ? __frcp_rn(g.post_nf) : 0.0f;
-    auto fin = [&](float y) {
-        y = __fmul_rn(y, g.divisor);
-        return post ? div_nf(y, g.post_nf, post_rnf) : y;
-    };
+    // one multiplication by divisor / nf instead of `* divisor` and the sink's `(0.0 + y) / nf` (see inv_pass1)
+    const float scale = g.post_nf != 0.0f ? (float)((double)g.divisor / (double)g.post_nf) : g.divisor;
+    const bool unit = scale == 1.0f;
+    auto fin = [&](float y) { return unit ? y : __fmul_rn(y, scale); };
     if (t == 0) s_item[0] = (int)atomicAdd(g.work + 2, 1u);
     __syncthreads();
     for (int it = 0;; it++) {
