@@ -149,6 +149,10 @@ struct Node {
     int u_ring = 0, u_pos = 0;      // u_ring = round_up(hist_pad + max_samples, 128)
     DevBuf Y;                       // [C x max_samples]
     std::vector<std::unique_ptr<DevBuf>> fft_work;  // persistent FFT kernel: work counter + per-CTA scratch, one per launch lane
+    DevBuf fdl;                     // short calls (UPC kernel): frequency-domain delay line, [pairs][P][2048] complex
+    bool fdl_valid = false;         // the previous call was a UPC call: the FDL holds the P-1 previous block spectra
+    bool upc_this_call = false;
+    int64_t upc_ctr = 0;            // running block counter (FDL slot = counter mod P)
     DevBuf H, taps_dev;
     DevBuf toep_tiles, toep_split;  // FIR_TOEPLITZ: Toeplitz tiles of the taps, hi/lo bf16 split of U
     int hist_pad = 0;
@@ -346,6 +350,8 @@ int clear_node_state(dspb_engine* e, Node& n) {
     if (n.U.p) CUDA_TRY(cudaMemset(n.U.p, 0, n.U.bytes));
     n.started = 0;
     n.u_pos = 0;
+    n.fdl_valid = false;
+    n.upc_ctr = 0;
     (void)e;
     return DSPB_OK;
 }
@@ -1004,7 +1010,9 @@ int ensure_resources(dspb_engine* e) {
         if (n.type == T_FIR && (n.fir_dirty || !n.Y.p)) {
             const int N = (int)n.taps.size();
             const int F = 1 << e->cfg.fir_fft_log2;
-            n.hist_pad = (int)round_up(std::max(N - 1, 4), 4);
+            // history kept in front of a call: N-1 samples; the UPC kernel re-primes its delay line from P whole blocks
+            const int upc_P = e->cfg.fir_mode == FIR_FFT ? fir_upc_partitions(N) : 0;
+            n.hist_pad = (int)round_up(std::max(std::max(N - 1, 4), upc_P * kUpcBlock), 4);
             if ((int64_t)n.hist_pad + maxn > (1ll << 30)) return fail(DSPB_ERR_INVALID, "max_samples too large for the FIR input ring");
             n.u_ring = (int)round_up(n.hist_pad + maxn, 128);
             int r = n.U.alloc((size_t)C * n.u_ring * 4, true, e->plan_only);
@@ -1016,6 +1024,12 @@ int ensure_resources(dspb_engine* e) {
             (void)F;
             r = n.taps_dev.alloc((size_t)N * 8, false, e->plan_only);
             if (r) return r;
+            if (upc_P) {
+                r = n.fdl.alloc(fir_upc_fdl_bytes(N, C), true, e->plan_only);
+                if (r) return r;
+            }
+            n.fdl_valid = false;
+            n.upc_ctr = 0;
             const bool toep = e->cfg.fir_mode == FIR_TOEPLITZ && N <= fir_toeplitz_max_taps();
             if (toep) {
                 r = n.toep_tiles.alloc(fir_toeplitz_tiles_bytes(N), false, e->plan_only);
@@ -1182,6 +1196,17 @@ int run_steps(dspb_engine* e, const float* const* d_in, float* const* d_out, int
                 }
                 fp.fft_work = f.fft_work[lane]->p;
             }
+            // short calls (1 or 2 blocks of 1024): uniformly partitioned convolution with a frequency-domain delay line.  Measured
+            // at 4096 channels: 62 / 101 / 141 us for 1 / 2 / 3 blocks against 92 - 104 us for the one 8192-point window the
+            // segment kernel needs for any call of up to 4096 samples.  DSPB_FIR_UPC=n: up to n blocks (0 = never).
+            static const int upc_max_blocks = getenv("DSPB_FIR_UPC") ? atoi(getenv("DSPB_FIR_UPC")) : 2;
+            const int upc_P = fir_upc_partitions(fp.n_taps);
+            f.upc_this_call = fp.mode == FIR_FFT && upc_P > 0 && f.fdl.p && n % kUpcBlock == 0 && n / kUpcBlock <= upc_max_blocks;
+            if (f.upc_this_call) {
+                fp.upc_fdl = f.fdl.p;
+                fp.upc_prime = f.fdl_valid ? 0 : upc_P - 1;
+                fp.upc_block0 = f.upc_ctr;
+            }
             int nl = 0;
             float* yp = s.fir_out_term >= 0 ? d_out[s.fir_out_term] : f.Y.p;
             const int64_t ys = s.fir_out_term >= 0 ? n : e->cfg.max_samples;
@@ -1197,7 +1222,13 @@ void advance_state(dspb_engine* e, int64_t n) {
     for (auto& np : e->nodes) {
         Node& nd = *np;
         if (nd.type == T_REVERB && nd.D > 0) nd.pos = (nd.pos + n) % nd.D;
-        if (nd.type == T_FIR) { nd.started += n; nd.u_pos = (int)((nd.u_pos + n) % nd.u_ring); }
+        if (nd.type == T_FIR) {
+            nd.started += n;
+            nd.u_pos = (int)((nd.u_pos + n) % nd.u_ring);
+            nd.fdl_valid = nd.upc_this_call;   // a call through the segment kernels leaves the delay line stale
+            if (nd.upc_this_call) nd.upc_ctr += n / kUpcBlock;
+            nd.upc_this_call = false;
+        }
     }
 }
 

@@ -775,6 +775,221 @@ __global__ void fir_spectrum_wide_kernel(const double* __restrict__ taps_rev, in
     Hout[(size_t)(q * kNTW + u) * 2 + (sreg & 1)] = make_float2((float)(re / kN2), (float)(im / kN2));
 }
 
+// ======================= uniformly partitioned convolution for short calls ("UPC" kernel) =======================
+// A call of 1024 samples still needs an 8192-point window with the kernels above (N - 1 = 4095 samples of history in front of
+// 1024 new ones): four times the transform work per output.  For such calls the impulse response is cut into P = ceil(N / 1024)
+// partitions of B = 1024 taps and the convolution runs block by block in the frequency domain (north_star's "uniformly
+// partitioned FFT convolution in shared memory"):
+//     X_b = FFT2048([block b-1, block b])                     one forward transform per new block, kept in a frequency-domain
+//     Y_b = sum_p X_(b-p) . H_p,  H_p = FFT2048([h_p, 0])     delay line (FDL) of the last P spectra per channel pair
+//     y_b = last 1024 samples of IFFT2048(Y_b)
+// Two channels share a complex transform as everywhere else.  One 128-thread CTA per channel pair walks the call's blocks in
+// order; 2048 points = radices 16 . 16 . 8, 19 KB of shared memory, so eight CTAs share an SM.  The FDL lives in global memory
+// ([pair][slot = block mod P][2048], written and read back in the middle pass's own register order); when the previous call
+// was not a UPC call the launch first recomputes the P-1 previous spectra from the time-domain ring ("prime" blocks).
+// Position p = k1 * 128 + k2 * 8 + s holds bin f = k1 + 16 k2 + 256 bitrev3(s).
+constexpr int kUB = 1024;                    // partition / block length
+constexpr int kUF = 2 * kUB;                 // transform size
+constexpr int kUNT = 128;                    // threads
+constexpr int kUPad = kUF + kUF / 8 + 8 * (kUF / 128);   // 2432 complex
+constexpr int kUT2 = 15 * 8;                 // W128^(j k), k = 1..15 major, j < 8
+constexpr int kUTw = kCoarse + kFine + kUT2;
+constexpr int kUMaxP = 4;
+__device__ __forceinline__ int padu(int p) { return p + (p >> 3) + ((p >> 7) << 3); }
+
+struct UpcArgs {
+    const float* U;
+    long long u_stride;
+    int u_ring, u_pos;
+    float* Y;
+    long long y_stride;
+    const float4* H;       // [P][2][4][128] float4: partition spectra in middle-pass order, scaled 1 / 2048
+    float4* fdl;           // [pairs][P][2][4][128] float4
+    const float2* Wg;      // compact twiddle table (coarse 512 | fine 32 | ...)
+    float scale;           // divisor (and the fused sink average), one multiplication
+    int c_begin, c_end;
+    int P, n_blocks, prime;
+    long long b0;          // running block counter of the call's first block (FDL slot = counter mod P)
+    int pair0;             // first channel pair of this launch inside the FDL
+};
+
+__global__ void __launch_bounds__(kUNT, 8)
+fir_upc_kernel(const __grid_constant__ UpcArgs g) {
+    extern __shared__ float2 smem_f2[];
+    C2<float>* a = reinterpret_cast<C2<float>*>(smem_f2);
+    C2<float>* tabs = a + kUPad;
+    const int t = threadIdx.x;
+    for (int i = t; i < kCoarse + kFine; i += kUNT) tabs[i] = C2<float>{g.Wg[i].x, g.Wg[i].y};
+    if (t < kUT2) {  // W128^(j k) = W512^(4 j k)
+        const int k = t / 8 + 1, j = t % 8;
+        const float2 w = g.Wg[(4 * j * k) & (kCoarse - 1)];
+        tabs[kCoarse + kFine + t] = C2<float>{w.x, w.y};
+    }
+    const Tw<float> W{tabs, tabs + kCoarse, nullptr};
+    const C2<float>* T2 = tabs + kCoarse + kFine;
+    const int pr = blockIdx.x;
+    const int chA = g.c_begin + 2 * pr, chB = chA + 1;
+    const bool hasB = chB < g.c_end;
+    const float* rowA = g.U + (long long)chA * g.u_stride;
+    const float* rowB = g.U + (long long)(hasB ? chB : chA) * g.u_stride;
+    float4* fdl = g.fdl + (size_t)(g.pair0 + pr) * g.P * 1024;
+    const bool unit = g.scale == 1.0f;
+    __syncthreads();
+    // twiddles of pass 1 / 1': W2048^(j q) = W16384^(8 j q), j = t; rebuilt in each of the two passes (84 instructions) rather
+    // than held in 30 registers for the whole launch: the kernel waits on memory, and 64 registers mean 8 CTAs per SM, not 6
+    auto twiddles1 = [&](C2<float> (&w1)[16]) {
+        const int j = t;
+        w1[1] = W.at2(8 * j); w1[2] = W.at2(16 * j); w1[4] = W.at2(32 * j); w1[8] = W.at2(64 * j);
+        w1[3] = cmul(w1[1], w1[2]); w1[5] = cmul(w1[1], w1[4]); w1[6] = cmul(w1[2], w1[4]); w1[7] = cmul(w1[3], w1[4]);
+#pragma unroll
+        for (int q = 9; q < 16; q++) w1[q] = cmul(w1[q - 8], w1[8]);
+    };
+    for (int blk = -g.prime; blk < g.n_blocks; blk++) {
+        const long long bidx = g.b0 + blk;
+        const int slot = (int)(((bidx % g.P) + g.P) % g.P);
+        const int wb = ring_slot(g.u_pos, (blk - 1) * kUB, g.u_ring);   // ring slot of window sample 0 (block blk - 1)
+        // The middle pass reads the P-1 previous spectra (16 KB each) from the delay line with nothing but a complex multiply
+        // between the loads (ncu: 68 % of the stall samples there, 80 % of them on the loads, L2 hit rate 9 %): pull them
+        // into L2 now, two passes ahead -- one 128-byte line per thread and slot.
+        if (blk >= 0)
+            for (int pp = 1; pp < g.P; pp++) {
+                const int sl2 = (int)((((bidx - pp) % g.P) + g.P) % g.P);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(fdl + (size_t)sl2 * 1024 + t * 8));
+            }
+        // ---- pass 1: global -> radix 16 over stride 128 -> shared
+        {
+            const int j = t;
+            C2<float> v[16];
+#pragma unroll
+            for (int r = 0; r < 16; r++) {
+                int sl = wb + j + r * 128;
+                if (sl >= g.u_ring) sl -= g.u_ring;
+                v[r] = C2<float>{__ldg(rowA + sl), __ldg(rowB + sl)};
+            }
+            fft_dif<16>(v);
+            C2<float> w1[16];
+            twiddles1(w1);
+            C2<float>* p = a + padu(j);   // padu(j + 128 q) = padu(j) + 152 q
+            p[0] = v[0];
+#pragma unroll
+            for (int s = 1; s < 16; s++) p[bitrev4(s) * 152] = cmul(v[s], w1[bitrev4(s)]);
+        }
+        __syncthreads();
+        // ---- pass 2: radix 16 over stride 8 inside each 128-block
+        {
+            const int b = t >> 3, j = t & 7;
+            C2<float>* p = a + padu(b * 128 + j);   // padu(base + 8 r) = padu(base) + 9 r
+            C2<float> v[16];
+#pragma unroll
+            for (int r = 0; r < 16; r++) v[r] = p[r * 9];
+            fft_dif<16>(v);
+            p[0] = v[0];
+#pragma unroll
+            for (int s = 1; s < 16; s++) p[bitrev4(s) * 9] = cmul(v[s], T2[(bitrev4(s) - 1) * 8 + j]);
+        }
+        __syncthreads();
+        // ---- middle: radix 8 on contiguous points; spectrum into the FDL; partitioned product; inverse radix 8
+#pragma unroll 1
+        for (int q = 0; q < 2; q++) {
+            const int u = t + kUNT * q;
+            C2<float>* p = a + padu(8 * u);   // 8 contiguous points, no pad inside
+            C2<float> v[8];
+#pragma unroll
+            for (int s = 0; s < 8; s++) v[s] = p[s];
+            fft_dif<8>(v);
+            float4* xs = fdl + ((size_t)(slot * 2 + q) * 4) * kUNT + t;
+#pragma unroll
+            for (int s2 = 0; s2 < 4; s2++) __stcg(xs + s2 * kUNT, make_float4(v[2 * s2].x, v[2 * s2].y, v[2 * s2 + 1].x, v[2 * s2 + 1].y));
+            if (blk < 0) continue;   // prime block: only its spectrum is needed
+            C2<float> acc[8];
+            {
+                const float4* h = g.H + ((size_t)(0 * 2 + q) * 4) * kUNT + t;
+#pragma unroll
+                for (int s2 = 0; s2 < 4; s2++) {
+                    const float4 hh = __ldg(h + s2 * kUNT);
+                    acc[2 * s2] = cmul(v[2 * s2], C2<float>{hh.x, hh.y});
+                    acc[2 * s2 + 1] = cmul(v[2 * s2 + 1], C2<float>{hh.z, hh.w});
+                }
+            }
+            for (int pp = 1; pp < g.P; pp++) {
+                const int sl2 = (int)((((bidx - pp) % g.P) + g.P) % g.P);
+                const float4* xo = fdl + ((size_t)(sl2 * 2 + q) * 4) * kUNT + t;
+                const float4* h = g.H + ((size_t)(pp * 2 + q) * 4) * kUNT + t;
+#pragma unroll
+                for (int s2 = 0; s2 < 4; s2++) {
+                    const float4 x = __ldcg(xo + s2 * kUNT);
+                    const float4 hh = __ldg(h + s2 * kUNT);
+                    const C2<float> m0 = cmul(C2<float>{x.x, x.y}, C2<float>{hh.x, hh.y});
+                    const C2<float> m1 = cmul(C2<float>{x.z, x.w}, C2<float>{hh.z, hh.w});
+                    acc[2 * s2] = acc[2 * s2] + m0;
+                    acc[2 * s2 + 1] = acc[2 * s2 + 1] + m1;
+                }
+            }
+            ifft_dit<8>(acc);
+#pragma unroll
+            for (int s = 0; s < 8; s++) p[s] = acc[s];
+        }
+        __syncthreads();
+        if (blk < 0) continue;
+        // ---- pass 2'
+        {
+            const int b = t >> 3, j = t & 7;
+            C2<float>* p = a + padu(b * 128 + j);
+            C2<float> v[16];
+            v[0] = p[0];
+#pragma unroll
+            for (int s = 1; s < 16; s++) v[s] = cmulc(p[bitrev4(s) * 9], T2[(bitrev4(s) - 1) * 8 + j]);
+            ifft_dit<16>(v);
+#pragma unroll
+            for (int r = 0; r < 16; r++) p[r * 9] = v[r];
+        }
+        __syncthreads();
+        // ---- pass 1': the last 1024 samples of the 2048-point result are this block's outputs
+        {
+            const int j = t;
+            const C2<float>* p = a + padu(j);
+            C2<float> v[16], w1[16];
+            twiddles1(w1);
+            v[0] = p[0];
+#pragma unroll
+            for (int s = 1; s < 16; s++) v[s] = cmulc(p[bitrev4(s) * 152], w1[bitrev4(s)]);
+            ifft_dit<16>(v);
+            float* outA = g.Y + (long long)chA * g.y_stride + (long long)blk * kUB - kUB;
+            float* outB = g.Y + (long long)(hasB ? chB : chA) * g.y_stride + (long long)blk * kUB - kUB;
+#pragma unroll
+            for (int r = 8; r < 16; r++) {
+                const int n = j + r * 128;   // >= 1024
+                outA[n] = unit ? v[r].x : __fmul_rn(v[r].x, g.scale);
+                if (hasB) outB[n] = unit ? v[r].y : __fmul_rn(v[r].y, g.scale);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Partition spectra for the UPC kernel, by direct f64 summation, in the middle pass's order:
+// float4 [((p * 2 + q) * 4 + s2) * 128 + t] = (H_p[f(8 u + 2 s2)], H_p[f(8 u + 2 s2 + 1)]), u = t + 128 q.
+__global__ void fir_spectrum_upc_kernel(const double* __restrict__ taps_rev, int N, int P, float2* __restrict__ Hout) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P * kUF) return;
+    const int p = idx / kUF, pos = idx % kUF;
+    const int k1 = pos >> 7, k2 = (pos >> 3) & 15, sreg = pos & 7;
+    const int f = k1 + 16 * k2 + 256 * bitrev3(sreg);
+    double re = 0.0, im = 0.0;
+    for (int n = 0; n < kUB; n++) {
+        const int tap = p * kUB + n;
+        if (tap >= N) break;
+        const int m = (int)(((long long)f * n) & (kUF - 1));
+        double sn, cs;
+        sincospi(-2.0 * (double)m / (double)kUF, &sn, &cs);
+        const double h = taps_rev[N - 1 - tap];
+        re += h * cs;
+        im += h * sn;
+    }
+    const int u = pos >> 3, q = u / kUNT, tt = u % kUNT, s2 = sreg >> 1;
+    Hout[((size_t)((p * 2 + q) * 4 + s2) * kUNT + tt) * 2 + (sreg & 1)] = make_float2((float)(re / kUF), (float)(im / kUF));
+}
+
 // ======================= packed variant: two sub-transforms per register pair =======================
 // One radix-2 decimation-in-frequency step turns the F = 8192 point transform of z into two INDEPENDENT
 // 4096-point transforms (E[n] = z[n] + z[n+4096] -> even bins, O[n] = (z[n] - z[n+4096]) W_F^n -> odd bins)
@@ -1160,7 +1375,10 @@ constexpr size_t kWorkHeader = 2048;  // [0] next, [1] done, [8 .. 264) per-SM s
 }  // namespace
 
 int fir_fft_max_taps() { return kF / 2 + 1; }
-size_t fir_fft_spectrum_bytes() { return (size_t)6 * kF * sizeof(float2); }  // H13 | packed-kernel order | H14 even | H14 odd | wide (2 F)
+// H13 | packed-kernel order | H14 even | H14 odd | wide (2 F) | UPC partitions (4 x 2048 = F)
+size_t fir_fft_spectrum_bytes() { return (size_t)7 * kF * sizeof(float2); }
+int fir_upc_partitions(int n_taps) { return n_taps <= kUMaxP * kUB ? (n_taps + kUB - 1) / kUB : 0; }
+size_t fir_upc_fdl_bytes(int n_taps, int channels) { return (size_t)((channels + 1) / 2) * fir_upc_partitions(n_taps) * kUF * sizeof(float2); }
 size_t fir_fft_work_bytes() { return kWorkHeader + (size_t)kMaxCtas * (kF / 2) * sizeof(float4); }
 static int effective_taps(int n) { return (n - 1 + 3) / 4 * 4 + 1; }  // Ne - 1 multiple of 4
 
@@ -1281,6 +1499,38 @@ int launch_fir_fft(const FirPlan& fp, const float* U, int64_t u_stride, float* Y
     return (int)cudaGetLastError();
 }
 
+// Short calls: uniformly partitioned convolution (see fir_upc_kernel).  fp.upc_* describe the FDL and the block counter.
+int launch_fir_upc(const FirPlan& fp, const float* U, int64_t u_stride, float* Y, int64_t y_stride, int c_begin, int c_end, int64_t T,
+                   cudaStream_t st, int* n_launches) {
+    const int P = fir_upc_partitions(fp.n_taps);
+    if (!P || T % kUB || !fp.upc_fdl || fp.hist_pad < P * kUB || fp.hist_pad + T > fp.u_ring) return (int)cudaErrorInvalidValue;
+    int rc = ensure_tables();
+    if (rc) return rc;
+    static std::atomic<bool> conf_dev[kMaxDevices];
+    std::atomic<bool>& conf = conf_dev[current_device_slot()];
+    const int smem = (kUPad + kUTw) * (int)sizeof(float2);
+    if (!conf.load(std::memory_order_acquire)) {
+        cudaError_t e = cudaFuncSetAttribute(fir_upc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        conf.store(true, std::memory_order_release);
+    }
+    UpcArgs g;
+    g.U = U; g.u_stride = u_stride; g.u_ring = fp.u_ring; g.u_pos = fp.u_pos;
+    g.Y = Y; g.y_stride = y_stride;
+    g.H = reinterpret_cast<const float4*>(fp.H + 6 * kF);
+    g.fdl = reinterpret_cast<float4*>(fp.upc_fdl);
+    g.Wg = g_tab.Wf;
+    g.scale = fp.post_nf != 0.0f ? (float)((double)fp.divisor / (double)fp.post_nf) : fp.divisor;
+    g.c_begin = c_begin; g.c_end = c_end;
+    g.P = P; g.n_blocks = (int)(T / kUB); g.prime = fp.upc_prime;
+    g.b0 = fp.upc_block0;
+    g.pair0 = c_begin / 2;
+    const int pairs = (c_end - c_begin + 1) / 2;
+    fir_upc_kernel<<<pairs, kUNT, smem, st>>>(g);
+    if (n_launches) *n_launches += 1;
+    return (int)cudaGetLastError();
+}
+
 int fir_prepare_spectrum(int log2F, const double* taps_rev_dev, int n_taps, float2* H_dev, void* stream) {
     if (log2F != kLog2F || n_taps > fir_fft_max_taps()) return (int)cudaErrorInvalidValue;
     int rc = ensure_tables();
@@ -1294,6 +1544,8 @@ int fir_prepare_spectrum(int log2F, const double* taps_rev_dev, int n_taps, floa
     fir_spectrum_kernel<<<1, kNT, smem, st>>>(taps_rev_dev, n_taps, g_tab.Wd, H_dev + 2 * kF, 0, 0.5 / kF);
     fir_spectrum_kernel<<<1, kNT, smem, st>>>(taps_rev_dev, n_taps, g_tab.Wd, H_dev + 3 * kF, 1, 0.5 / kF);
     fir_spectrum_wide_kernel<<<kN2 / 128, 128, 0, st>>>(taps_rev_dev, n_taps, H_dev + 4 * kF);
+    if (const int P = fir_upc_partitions(n_taps))
+        fir_spectrum_upc_kernel<<<(P * kUF + 127) / 128, 128, 0, st>>>(taps_rev_dev, n_taps, P, H_dev + 6 * kF);
     return (int)cudaGetLastError();
 }
 

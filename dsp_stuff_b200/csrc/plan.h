@@ -161,6 +161,10 @@ struct FirPlan {
     int u_ring;           // U rows are rings of u_ring samples (multiple of 128, >= hist_pad + T): sample i of this call
     int u_pos;            // (i in [-hist_pad, T)) lives at slot (u_pos + i) mod u_ring
     void* fft_work;       // FIR_FFT: per-launch-lane work area of the persistent kernel (fir_fft_work_bytes())
+    // FIR_FFT, short calls: uniformly partitioned convolution (fir_fft.cu fir_upc_kernel)
+    void* upc_fdl = nullptr;      // frequency-domain delay line [pairs][P][2048] float2, or null: not eligible
+    int upc_prime = 0;            // previous blocks whose spectra must be recomputed from the ring first (0 .. P - 1)
+    long long upc_block0 = 0;     // running block counter of this call's first block
     const float2* H;      // [2F] spectrum of h pre-scaled by 1/F: [0, F) in the scalar kernel's output order, then F/2 float4
                           // (even bin, odd bin) pairs in the packed kernel's order
     const double* taps;   // [N] reversed taps (f64) for the warm-up path
@@ -181,6 +185,9 @@ int fir_prepare_spectrum(int log2F, const double* taps_rev_dev, int n_taps, floa
 int fir_fft_max_taps();
 size_t fir_fft_spectrum_bytes();   // H buffer of one tap set (all spectrum tables of the FFT kernels)
 size_t fir_fft_work_bytes();       // one launch lane's work area (work counter + per-CTA scratch)
+int fir_upc_partitions(int n_taps);                      // 1024-tap partitions of the UPC kernel, 0 = impulse response too long
+size_t fir_upc_fdl_bytes(int n_taps, int channels);
+constexpr int kUpcBlock = 1024;
 // device-boundary format steps (boundary.cu): stereo fold a + b, mono -> stereo duplicate; flat [C * n] streams
 int launch_fold_stereo(const float* interleaved, float* mono, long long total_mono, cudaStream_t st);
 int launch_dup_stereo(const float* mono, float* interleaved, long long total_mono, cudaStream_t st);

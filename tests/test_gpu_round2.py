@@ -245,3 +245,31 @@ def test_async_host_calls_equal_blocking_calls(oracle_mod):
     b.sync()
     assert_bit_exact(out[0].numpy(), ya[0], "before the setter")
     assert_bit_exact(out[1].numpy(), ya[1], "after the setter")
+
+
+@pytest.mark.parametrize("n_taps,chunks", [
+    (4096, [1024] * 10),                                  # BASELINE block size as the call size: P = 4 partitions
+    (4096, [2048, 1024, 3072, 1024, 128 * 5, 1024, 1024, 8192, 1024, 2048]),   # UPC calls between segment-kernel calls: re-priming
+    (3000, [1024] * 6 + [3072, 2048]),                    # last partition only partly filled
+    (1024, [1024] * 5),                                   # P = 1: no delay line reads
+    (700, [2048, 1024, 1024]),
+    (1, [1024, 1024]),
+])
+def test_uniformly_partitioned_fir_on_short_calls(oracle_mod, n_taps, chunks):
+    """Calls of 1 or 2 blocks of 1024 samples run the uniformly partitioned convolution (frequency-domain delay line); anything
+    else the segment kernels.  Same tolerance as every FFT path, warm-up samples bit-exact."""
+    spec = S.config4(n_taps)
+    C = 5
+    x = S.noise(C, sum(chunks))
+    got, ref, eng = run_both(oracle_mod, spec, x, chunks=chunks, fir_mode=FIR_FFT)
+    rel, dbfs = assert_audio_close(got[0], ref[0], what=f"upc N={n_taps}")
+    w = min(sum(chunks), n_taps - 1)
+    assert_bit_exact(got[0][:, :w], ref[0][:, :w], "fir warm-up")
+    print(f"upc N={n_taps}: peak-relative {rel:.2e}, rms {dbfs:.1f} dBFS")
+
+
+def test_target_chain_in_1024_sample_calls(oracle_mod):
+    spec = S.target_chain(4096)
+    x = S.noise(6, 1024 * 14)
+    got, ref, eng = run_both(oracle_mod, spec, x, chunks=[1024] * 14, fir_mode=FIR_FFT)
+    assert_audio_close(got[0], ref[0], what="target chain, 1024-sample calls")
