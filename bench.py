@@ -612,7 +612,7 @@ def main():
                                             "note": "the two directions alone, all ranks copying at once (max over ranks): the host-side bound of e2e"}}
         if gather_ms:
             line["gather_to_rank0_ms"] = gather_ms
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # rank 0 at N = 1 only; at N > 1 this rank is pinned to its core slice
             line["cpu_baseline"] = cpu_baseline(spec, args.cpu_seconds)
         emit(line)
     if world > 1:

@@ -393,3 +393,58 @@ class NpOracle:
 
     def process_n(self, n: int) -> List[np.ndarray]:
         return self.process([], n)
+
+
+class NpResampler:
+    """Independent restatement (pure Python / numpy scalars) of the playback-side converter: dasp_signal 0.11.0
+    `Converter::from_hz_to_hz(CountingSignal, Sinc::new(Fixed::from([0.0; 16])), 48_000.0, target)` as built at devices.rs:550-556
+    and driven by `do_write_2` (devices.rs:443-500).  Restated from the published crates (parity UNPINNED); cross-checked
+    bit for bit against the C++ oracle's restatement in tests/test_oracle_cross.py.  One channel at a time, slow."""
+
+    DEPTH = 8
+
+    def __init__(self, channels: int, target_hz: float, source_hz: float = 48000.0):
+        self.C = channels
+        self.ratio = float(source_hz) / float(target_hz)
+        self.value = [0.0] * channels                      # Converter::interpolation_value
+        self.frames = [[F(0.0)] * 16 for _ in range(channels)]   # ring_buffer::Fixed: index 0 = oldest
+        self.idx = [0] * channels                          # Sinc::idx
+
+    def _interpolate(self, frames, idx, x):
+        depth = self.DEPTH
+        nl, nr = idx, idx + 1
+        rightmost, leftmost = nl + depth, nr - depth
+        max_depth = (16 - depth) if rightmost >= 16 else ((depth + leftmost) if leftmost < 0 else depth)
+        v = F(0.0)
+        for n in range(max_depth):
+            for phi, i in ((x + n, nl - n), ((1.0 - x) + n, nr + n)):
+                a = math.pi * phi
+                first = 1.0 if a == 0.0 else math.sin(a) / a
+                second = 0.5 + 0.5 * math.cos(a / depth)
+                v = F(v + F(first * second * float(frames[i % 16])))   # Fixed indexes modulo its length
+        return v
+
+    def process(self, mono, n_out: int):
+        x = np.ascontiguousarray(mono, dtype=F)
+        out = np.zeros((self.C, n_out, 2), F)
+        used = 0
+        for c in range(self.C):
+            index = 0
+            fr, idx, val = self.frames[c], self.idx[c], self.value[c]
+            for m in range(n_out):
+                while val >= 1.0:
+                    f = F(0.0)
+                    if index < x.shape[1]:
+                        f = x[c, index]
+                        index += 1
+                    fr = fr[1:] + [f]           # push: the oldest frame drops out
+                    if idx < self.DEPTH:
+                        idx += 1
+                    val -= 1.0
+                y = self._interpolate(fr, idx, val)
+                val += self.ratio
+                out[c, m, 0] = y
+                out[c, m, 1] = y
+            self.frames[c], self.idx[c], self.value[c] = fr, idx, val
+            used = index
+        return out, used

@@ -273,3 +273,30 @@ def test_value_spilled_and_reused_in_one_step_is_not_prefetched(lib):
                 stored.add(o[1].rstrip("*"))
             if o[0] == OP_LOADG and o[1].rstrip("*") in stored:
                 assert not o[1].endswith("*"), ("prefetched although stored earlier in the same program", ops)
+
+
+def test_iir_mode_lowers_to_scan_segments_in_planning_mode(lib):
+    """dspb_config::iir_mode = 1 (opt-in time-parallel recurrences): in planning mode every filter is assumed to pass the
+    probe, so the schedule shows the scan verdict, no transposition tile, and as many CTAs as fill the machine."""
+    import re
+
+    from dsp_stuff_b200 import signals as S
+    from dsp_stuff_b200.engine import Engine, EngineError
+
+    for C, G in [(256, 1), (512, 2), (4096, 16)]:
+        e = Engine(C, block=1024, max_samples=24576, device=-1, iir_mode=1)
+        S.config3().apply(e)
+        plan = e.describe_plan()
+        assert "time-parallel scan (probe error" in plan and "exact, lane=channel" not in plan, plan
+        assert re.search(rf"fused segment: G={G} channels", plan), plan
+    e = Engine(256, block=1024, max_samples=24576, device=-1)      # default: exact
+    S.config3().apply(e)
+    assert "time-parallel" not in e.describe_plan()
+    e = Engine(64, device=-1, iir_mode=1)                           # an envelope stays sequential -> the biquad next to it too
+    g = S.config3()
+    g.nodes.insert(3, type(g.nodes[0])(7, "envelope"))
+    g.links = [l for l in g.links if not (l[0] == 2 and l[2] == 3)] + [(2, "out", 7, "in"), (7, "out", 3, "in")]
+    g.apply(e)
+    assert "exact after all" in e.describe_plan()
+    with pytest.raises(EngineError):
+        Engine(4, device=-1, iir_mode=5)

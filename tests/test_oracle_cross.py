@@ -151,3 +151,20 @@ def test_config5_graph_with_tanh(oracle_mod):
     x = S.noise(2, 128 * 100)
     ya, yb = both(oracle_mod, S.config5(n_taps=32), x, 2)
     assert_audio_close(yb[0], ya[0], what="config5 graph")   # path A holds a Tanh distortion (libm vs numpy)
+
+
+@pytest.mark.parametrize("target", [44100.0, 96000.0, 48000.0, 22050.0])
+def test_resampler_restatements_agree(oracle_mod, target):
+    """dasp Converter + Sinc<[f32; 16]> (devices.rs:443-500, 550-556): the C++ and the Python restatement, two calls each."""
+    from oracle.np_oracle import NpResampler
+
+    x = S.noise(2, 700, seed=11)
+    a, b = oracle_mod.Resampler(2, target), NpResampler(2, target)
+    off_a = off_b = 0
+    for n_out in (300, 150):
+        ya, ua = a.process(x[:, off_a:], n_out)
+        yb, ub = b.process(x[:, off_b:], n_out)
+        assert ua == ub
+        assert_bit_exact(yb.reshape(2, -1), ya.reshape(2, -1), f"resampler {target}")
+        off_a += ua
+        off_b += ub
