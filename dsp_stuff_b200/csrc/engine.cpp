@@ -174,6 +174,7 @@ struct Step {
     struct Bind { int kind; int idx; };  // kind 0 ext-in, 1 ext-out, 2 scratch, 3 fir U (idx=node), 4 fir Y (idx=node)
     std::vector<Bind> binds;             // parallel to prog.bufs
     std::vector<int> ring_nodes;         // parallel to prog.rings
+    std::vector<int> nodes;              // STEP_FUSED: the nodes (engine indices) whose ops this segment holds, in order
     std::string text;                    // human-readable listing
 };
 
@@ -379,18 +380,38 @@ struct Lowerer {
     std::set<int> fused_sinks;                    // output terminals written directly by a FIR step
     std::vector<ScanTab> scan_tabs;               // scan tables of the current fused step (Op::mode = index + 1)
     std::string err;
+    // A graph region between two FIR nodes normally becomes ONE fused segment.  When it exceeds what one Program holds
+    // (ops, global buffers, states, rings, virtual vregs, shared memory) the segment is closed in front of a node and the
+    // rest starts a new one; values that cross the cut travel through global scratch like values that cross a FIR step.
+    // lower_graph() retries with one more cut until every segment fits.
+    std::set<int> split_before;                   // nodes in front of which the open segment is closed
+    int want_split = -1;                          // set with `err` when one more cut would help
+    std::vector<int> cur_nodes;                   // nodes that emitted ops into the open segment
+    int cur_node = -1;
 
     explicit Lowerer(dspb_engine& en) : e(en) {}
 
+    // A per-segment limit was hit while lowering `cur_node`: everything before it fitted, so cut in front of it.
+    void overflow(const char* what) {
+        if (!err.empty()) return;
+        err = what;
+        if (!cur_nodes.empty() && cur_nodes.front() != cur_node) want_split = cur_node;
+    }
     int buf_slot(int kind, int idx) {
         for (size_t i = 0; i < cur.binds.size(); i++)
             if (cur.binds[i].kind == kind && cur.binds[i].idx == idx) return (int)i;
-        if ((int)cur.binds.size() >= kMaxBufs) { err = "segment uses too many global buffers"; return 0; }
+        if ((int)cur.binds.size() >= kMaxBufs) { overflow("segment uses too many global buffers"); return 0; }
         cur.binds.push_back({kind, idx});
         return (int)cur.binds.size() - 1;
     }
+    int new_vreg() {
+        if (next_vreg >= 0xFF) { overflow("segment has too many intermediate values"); return 0; }  // 0xFF names the accumulator
+        return next_vreg++;
+    }
     void emit(Op op, const std::string& s) {
-        if ((int)ops.size() >= kMaxOps - 1) { err = "segment has too many ops"; return; }
+        // bound on the UNFOLDED listing only (finish_vregs folds the fan-in prologues, typically 2-3 ops into one); the
+        // limit that matters, kMaxOps of the folded Program, is checked in close_fused
+        if ((int)ops.size() >= 4 * kMaxOps) { overflow("segment has too many ops"); return; }
         ops.push_back(op);
         txt.push_back(s);
     }
@@ -468,7 +489,7 @@ struct Lowerer {
             emit(o, "G" + std::to_string(o.buf) + " = acc                    ; scratch (crosses a step)");
         } else {
             v.where = Value::VREG;
-            v.id = next_vreg++;
+            v.id = new_vreg();
             Op o = mk(OP_SAVEV);
             o.vreg = (uint8_t)v.id;
             emit(o, "v" + std::to_string(v.id) + " = acc");
@@ -476,7 +497,7 @@ struct Lowerer {
         return v;
     }
     int temp_save(const std::string& what) {
-        int id = next_vreg++;
+        int id = new_vreg();
         Op o = mk(OP_SAVEV);
         o.vreg = (uint8_t)id;
         emit(o, "v" + std::to_string(id) + " = acc                    ; " + what);
@@ -581,9 +602,16 @@ int Lowerer::finish_vregs(Step& st, std::vector<Op>& o, std::vector<std::string>
 }
 
 void Lowerer::close_fused() {
-    if (ops.empty()) { cur = Step(); txt.clear(); next_vreg = 0; return; }
+    if (ops.empty() || !err.empty()) { cur = Step(); ops.clear(); txt.clear(); cur_nodes.clear(); next_vreg = 0; return; }
     cur.kind = STEP_FUSED;
     finish_vregs(cur, ops, txt);
+    if ((int)ops.size() > kMaxOps - 1) {  // the folded program does not fit: cut the segment in the middle and lower again
+        err = "segment has too many ops";
+        if (cur_nodes.size() >= 2) want_split = cur_nodes[cur_nodes.size() / 2];
+        return;
+    }
+    cur.nodes = cur_nodes;
+    cur_nodes.clear();
     Program& P = cur.prog;
     P.n_ops = (int)ops.size();
     P.needs_tile = 0;
@@ -703,6 +731,13 @@ void Lowerer::close_fused() {
             m += b;
         }
         cur.text += m + "\n";
+        m = "    buffers:";   // what each g<slot> is bound to at launch: terminals, scratch between segments, a FIR node's input ring / output
+        for (size_t i = 0; i < cur.binds.size(); i++) {
+            static const char* kKind[] = {"in", "out", "scratch", "firU#", "firY#"};
+            const int kind = cur.binds[i].kind, idx = cur.binds[i].idx;
+            m += " g" + std::to_string(i) + "=" + kKind[kind] + std::to_string(kind >= 3 ? (long long)e.nodes[idx]->id : (long long)idx);
+        }
+        cur.text += m + "\n";
     }
     steps.push_back(cur);
     cur = Step();
@@ -719,6 +754,7 @@ int Lowerer::lower() {
     {
         int s = 0;
         for (int ni : e.order) {
+            if (split_before.count(ni)) s += 1;      // a cut: this node opens a new fused step
             node_step[ni] = s;
             if (e.nodes[ni]->type == T_FIR) s += 2;  // fused step s, FIR step s+1, next fused s+2
         }
@@ -739,6 +775,15 @@ int Lowerer::lower() {
         Node& nd = *e.nodes[ni];
         const NodeType& nt = kNodeTypes[nd.type];
         const std::string tag = std::string(nt.cfg_name) + "#" + std::to_string(nd.id);
+        if (split_before.count(ni)) {
+            close_fused();
+            if (!err.empty()) return DSPB_ERR_INVALID;
+            logical_step += 1;
+            state_slot = 0;
+        }
+        cur_node = ni;
+        const size_t ops_before = ops.size();
+        if (nd.type != T_FIR) cur_nodes.push_back(ni);   // dropped again below if the node emits nothing
         auto out_value = [&](int port) {
             // like save_value but with the logical step numbering
             Value v;
@@ -777,7 +822,7 @@ int Lowerer::lower() {
             }
         };
         auto alloc_state = [&](Op& op) -> int {
-            if (state_slot >= kMaxStates) { err = "too many stateful nodes in one graph step"; return -1; }
+            if (state_slot >= kMaxStates) { overflow("too many stateful nodes in one segment"); return -1; }
             op.aux = (uint16_t)state_slot;
             cur.prog.states[state_slot] = nd.state.p;
             return state_slot++;
@@ -800,11 +845,14 @@ int Lowerer::lower() {
                 emit(o, "G" + std::to_string(o.buf) + " = acc                    ; output terminal " + std::to_string(t));
             } break;
             case T_FIR: {
+                cur_nodes.push_back(ni);
                 emit_avg(ni, 0);
                 Op o = mk(OP_STOREG);
                 o.buf = (uint8_t)buf_slot(3, ni);
                 emit(o, "G" + std::to_string(o.buf) + " = acc                    ; " + tag + " input (+history)");
+                if (!err.empty()) return DSPB_ERR_INVALID;
                 close_fused();
+                if (!err.empty()) return DSPB_ERR_INVALID;
                 Step fs;
                 fs.kind = STEP_FIR;
                 fs.fir_node = ni;
@@ -971,7 +1019,7 @@ int Lowerer::lower() {
                     case T_REVERB:
                         op.code = OP_COMB;
                         op.p[0] = nd.f32[1];
-                        if ((int)cur.ring_nodes.size() >= kMaxRings) { err = "too many reverb nodes in one step"; return DSPB_ERR_INVALID; }
+                        if ((int)cur.ring_nodes.size() >= kMaxRings) { overflow("too many reverb nodes in one segment"); return DSPB_ERR_INVALID; }
                         op.aux = (uint16_t)cur.ring_nodes.size();
                         cur.ring_nodes.push_back(ni);
                         snprintf(b, sizeof b, "acc += ring*%g ; ring = acc   (D=%lld)", nd.f32[1], (long long)nd.D);
@@ -987,6 +1035,7 @@ int Lowerer::lower() {
             } break;
         }
         if (!err.empty()) return DSPB_ERR_INVALID;
+        if (nd.type != T_FIR && ops.size() == ops_before && !cur_nodes.empty() && cur_nodes.back() == ni) cur_nodes.pop_back();
     }
     close_fused();
     return err.empty() ? DSPB_OK : DSPB_ERR_INVALID;
@@ -1059,19 +1108,40 @@ int ensure_resources(dspb_engine* e) {
 int lower_graph(dspb_engine* e) {
     int r = ensure_resources(e);
     if (r) return r;
-    Lowerer L(*e);
-    r = L.lower();
-    if (r) return fail(r, "lowering failed: %s", L.err.c_str());
-    e->steps = std::move(L.steps);
-    while ((int)e->scratch.size() < L.n_scratch) {
+    // Lower; when a segment exceeds what one Program / one CTA holds, cut it in front of the node the Lowerer names and
+    // lower again (each attempt adds one cut, so this ends after at most one attempt per node).
+    std::set<int> cuts;
+    int n_scratch = 0;
+    for (;;) {
+        Lowerer L(*e);
+        L.split_before = cuts;
+        r = L.lower();
+        if (r) {
+            if (L.want_split >= 0 && cuts.insert(L.want_split).second) continue;
+            return fail(r, "lowering failed: %s", L.err.c_str());
+        }
+        int cut = -1;
+        for (auto& st : L.steps)
+            if (st.kind == STEP_FUSED && fused_smem_bytes(st.prog, st.G) > 200 * 1024) {
+                if (st.nodes.size() < 2)
+                    return fail(DSPB_ERR_INVALID, "fused segment needs %d B of shared memory (too many live values)", fused_smem_bytes(st.prog, st.G));
+                cut = st.nodes[st.nodes.size() / 2];
+                break;
+            }
+        if (cut >= 0) {
+            if (cuts.insert(cut).second) continue;
+            return fail(DSPB_ERR_INVALID, "fused segment does not fit in shared memory (too many live values)");
+        }
+        e->steps = std::move(L.steps);
+        n_scratch = L.n_scratch;
+        break;
+    }
+    while ((int)e->scratch.size() < n_scratch) {
         auto b = std::make_unique<DevBuf>();
         r = b->alloc((size_t)e->cfg.channels * e->cfg.max_samples * 4, false, e->plan_only);
         if (r) return r;
         e->scratch.push_back(std::move(b));
     }
-    for (auto& st : e->steps)
-        if (st.kind == STEP_FUSED && fused_smem_bytes(st.prog, st.G) > 200 * 1024)
-            return fail(DSPB_ERR_INVALID, "fused segment needs %d B of shared memory (too many live values)", fused_smem_bytes(st.prog, st.G));
     e->lowered = true;
     return DSPB_OK;
 }

@@ -79,6 +79,59 @@ def _io(g: GraphSpec, first: int, last: int) -> GraphSpec:
     return g
 
 
+def random_graph(seed, n_nodes=None):
+    """A random DAG over the FMA-free node types: every input port gets 1-3 links from earlier nodes (fan-in averaging with
+    different divisors, fan-out by reuse), control ports are sometimes driven, two sinks."""
+    rng = np.random.default_rng(seed)
+    from .graph import NODE_PORTS as ports
+
+    g = GraphSpec().node(100, "input").node(101, "input")
+    outs = [(100, "out"), (101, "out")]
+    kinds = ["gain", "distort", "biquad", "low_pass", "high_pass", "reverb", "add", "mix", "mux", "demux", "envelope", "fir"]
+    for nid in range(int(rng.integers(4, 9)) if n_nodes is None else n_nodes):
+        t = kinds[int(rng.integers(len(kinds)))]
+        params = {}
+        taps = None
+        if t == "gain":
+            params = dict(level=float(rng.uniform(0.2, 3.0)))
+        elif t == "distort":
+            params = dict(mode=["HardClip", "SoftClip", "RecipSoftClip", "Square", "Chebyshev4"][int(rng.integers(5))], level=float(rng.uniform(0.0, 6.0)))
+        elif t == "biquad":
+            r, th = float(rng.uniform(0.1, 0.95)), float(rng.uniform(0.1, 3.0))
+            params = dict(a0=float(rng.uniform(0.5, 2.0)), a1=-2 * r * np.cos(th), a2=r * r, b0=float(rng.uniform(0.1, 1.0)), b1=float(rng.uniform(-0.5, 0.5)), b2=float(rng.uniform(-0.5, 0.5)))
+        elif t in ("low_pass", "high_pass"):
+            params = dict(ratio=float(rng.uniform(0.0, 0.99)))
+        elif t == "reverb":
+            params = dict(seconds=float(rng.uniform(0.003, 0.012)), decay=float(rng.uniform(0.1, 0.9)))
+        elif t == "mix":
+            params = dict(ratio=float(rng.uniform(0, 1)))
+        elif t == "mux":
+            params = dict(in_port=["A", "B"][int(rng.integers(2))])
+        elif t == "demux":
+            params = dict(out_port=["A", "B"][int(rng.integers(2))])
+        elif t == "envelope":
+            params = dict(attack=float(rng.integers(0, 50)), release=float(rng.integers(0, 400)))
+        elif t == "fir":
+            params = dict(mode=["Average", "Balanced"][int(rng.integers(2))])
+            taps = rng.uniform(-1, 1, int(rng.integers(1, 40)))
+        g.node(nid, t, taps=taps, **params)
+        ins, node_outs = ports[t]
+        for p in ins:
+            control = p not in ("in", "a", "b")
+            if control and rng.uniform() < 0.6:
+                continue   # slider value
+            for _ in range(int(rng.integers(1, 4)) if not control else 1):
+                s, sp = outs[int(rng.integers(len(outs)))]
+                g.link(s, sp, nid, p)
+        outs += [(nid, q) for q in node_outs]
+    g.node(200, "output").node(201, "output")
+    for sink in (200, 201):
+        for _ in range(int(rng.integers(1, 4))):
+            s, sp = outs[int(rng.integers(2, len(outs)))] if len(outs) > 2 else outs[0]
+            g.link(s, sp, sink, "in")
+    return g
+
+
 def config1() -> GraphSpec:
     g = GraphSpec()
     g.node(0, "gain", level=2.0).node(1, "distort", mode="SoftClip", level=4.0)

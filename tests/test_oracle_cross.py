@@ -170,64 +170,24 @@ def test_resampler_restatements_agree(oracle_mod, target):
         off_b += ub
 
 
-def _random_graph(seed):
-    """A random DAG over the FMA-free node types: every input port gets 1-3 links from earlier nodes (fan-in averaging with
-    different divisors, fan-out by reuse), control ports are sometimes driven, two sinks."""
-    rng = np.random.default_rng(seed)
-    g = GraphSpec().node(100, "input").node(101, "input")
-    outs = [(100, "out"), (101, "out")]
-    kinds = ["gain", "distort", "biquad", "low_pass", "high_pass", "reverb", "add", "mix", "mux", "demux", "envelope", "fir"]
-    ports = __import__("dsp_stuff_b200").NODE_PORTS
-    for nid in range(int(rng.integers(4, 9))):
-        t = kinds[int(rng.integers(len(kinds)))]
-        params = {}
-        taps = None
-        if t == "gain":
-            params = dict(level=float(rng.uniform(0.2, 3.0)))
-        elif t == "distort":
-            params = dict(mode=["HardClip", "SoftClip", "RecipSoftClip", "Square", "Chebyshev4"][int(rng.integers(5))], level=float(rng.uniform(0.0, 6.0)))
-        elif t == "biquad":
-            r, th = float(rng.uniform(0.1, 0.95)), float(rng.uniform(0.1, 3.0))
-            params = dict(a0=float(rng.uniform(0.5, 2.0)), a1=-2 * r * np.cos(th), a2=r * r, b0=float(rng.uniform(0.1, 1.0)), b1=float(rng.uniform(-0.5, 0.5)), b2=float(rng.uniform(-0.5, 0.5)))
-        elif t in ("low_pass", "high_pass"):
-            params = dict(ratio=float(rng.uniform(0.0, 0.99)))
-        elif t == "reverb":
-            params = dict(seconds=float(rng.uniform(0.003, 0.012)), decay=float(rng.uniform(0.1, 0.9)))
-        elif t == "mix":
-            params = dict(ratio=float(rng.uniform(0, 1)))
-        elif t == "mux":
-            params = dict(in_port=["A", "B"][int(rng.integers(2))])
-        elif t == "demux":
-            params = dict(out_port=["A", "B"][int(rng.integers(2))])
-        elif t == "envelope":
-            params = dict(attack=float(rng.integers(0, 50)), release=float(rng.integers(0, 400)))
-        elif t == "fir":
-            params = dict(mode=["Average", "Balanced"][int(rng.integers(2))])
-            taps = rng.uniform(-1, 1, int(rng.integers(1, 40)))
-        g.node(nid, t, taps=taps, **params)
-        ins, node_outs = ports[t]
-        for p in ins:
-            control = p not in ("in", "a", "b")
-            if control and rng.uniform() < 0.6:
-                continue   # slider value
-            for _ in range(int(rng.integers(1, 4)) if not control else 1):
-                s, sp = outs[int(rng.integers(len(outs)))]
-                g.link(s, sp, nid, p)
-        outs += [(nid, q) for q in node_outs]
-    g.node(200, "output").node(201, "output")
-    for sink in (200, 201):
-        for _ in range(int(rng.integers(1, 4))):
-            s, sp = outs[int(rng.integers(2, len(outs)))] if len(outs) > 2 else outs[0]
-            g.link(s, sp, sink, "in")
-    return g
-
-
 @pytest.mark.parametrize("seed", range(24))
 def test_random_graphs_bit_exact(oracle_mod, seed):
     """Random DAGs (fan-in of 1-3 links, fan-out, control ports, demux zeros, nested recurrences): the two restatements agree
     bit for bit, sample for sample, across three calls."""
-    g = _random_graph(seed)
+    g = S.random_graph(seed)
     xs = [S.noise(2, 128 * 9, seed=seed + 1), S.sweep(2, 128 * 9) * 1.5]
     ya, yb = both(oracle_mod, g, xs, 2, chunks=3)
     for k in range(2):
         assert_bit_exact(yb[k], ya[k], f"random graph {seed}, sink {k}")
+
+
+@pytest.mark.parametrize("seed,n_nodes", [(2000, 30), (2000, 43), (2001, 57), (2001, 69)])
+def test_large_random_graphs_bit_exact(oracle_mod, seed, n_nodes):
+    """The graphs tests/test_gpu_zz_random_graphs.py runs on the GPU (cut into up to 15 segments there): the two restatements
+    agree on them first."""
+    g = S.random_graph(seed, n_nodes)
+    xs = [S.noise(3, 128 * 9, seed=seed + 1), S.sweep(3, 128 * 9) * 1.5]
+    ya, yb = both(oracle_mod, g, xs, 3, chunks=3)
+    for k in range(2):
+        assert np.isfinite(ya[k]).all() and 0.05 < np.abs(ya[k]).max() < 100
+        assert_bit_exact(yb[k], ya[k], f"{n_nodes}-node random graph {seed}, sink {k}")
