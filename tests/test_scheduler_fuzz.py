@@ -173,3 +173,19 @@ def test_a_single_node_that_cannot_fit_still_fails_loudly():
     with pytest.raises(EngineError) as ei:
         plan_of(g, 4)
     assert "too many ops" in str(ei.value)
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_saved_graph_round_trip_lowers_to_the_same_plan(seed):
+    """GraphSpec -> saved-graph JSON -> the C++ loader (dspb_load_graph_json) and -> the Python parser -> builder calls: all
+    three routes must produce the same schedule, parameter for parameter (the listing prints every coefficient)."""
+    from dsp_stuff_b200 import GraphSpec
+    from dsp_stuff_b200.engine import Engine
+
+    g = S.random_graph(seed, None if seed < 15 else 10 + seed)
+    text = g.to_json()
+    plans = [plan_of(g, 64), plan_of(GraphSpec.from_json(text), 64)]
+    e = Engine(64, block=128, max_samples=128 * 9, device=-1)
+    e.load_graph_json(text)
+    plans.append(e.describe_plan())
+    assert plans[0] == plans[1] == plans[2]
