@@ -999,7 +999,13 @@ int Lowerer::lower() {
                         std::string how = " exact, lane=channel";
                         if (e.cfg.iir_mode == 1) {
                             char v[96];
-                            if ((int)scan_tabs.size() < kMaxScan && scan_qualifies(op, tab, e.plan_only)) {
+                            if (scan_qualifies(op, tab, e.plan_only)) {
+                                // a Program holds kMaxScan scan tables; a fifth qualifying filter would stay sequential and
+                                // (all or nothing, close_fused) demote the other four with it: cut the segment here instead
+                                if ((int)scan_tabs.size() >= kMaxScan) {
+                                    overflow("segment has more time-parallel recurrences than one Program holds");
+                                    return DSPB_ERR_INVALID;
+                                }
                                 scan_tabs.push_back(tab);
                                 op.mode = (uint8_t)scan_tabs.size();
                                 snprintf(v, sizeof v, " time-parallel scan (probe error %.2g <= %.2g)", tab.probe_err, kScanGate);

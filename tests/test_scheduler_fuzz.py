@@ -189,3 +189,22 @@ def test_saved_graph_round_trip_lowers_to_the_same_plan(seed):
     e.load_graph_json(text)
     plans.append(e.describe_plan())
     assert plans[0] == plans[1] == plans[2]
+
+
+def test_scan_mode_cuts_at_the_scan_table_limit():
+    """iir_mode = 1: a Program holds four scan tables.  A fifth qualifying filter used to stay sequential and, all or nothing,
+    take the other four back to exact with it; now the segment is cut so that every filter stays time-parallel."""
+    from dsp_stuff_b200 import GraphSpec
+
+    g = GraphSpec().node(100, "input").node(101, "output")
+    prev = 100
+    for i in range(10):
+        g.node(i, "low_pass", ratio=0.5 + 0.04 * i)
+        g.link(prev, "out", i, "in")
+        prev = i
+    g.link(prev, "out", 101, "in")
+    plan = plan_of(g, 256, iir_mode=1)
+    check_dataflow(plan, 1)
+    assert plan.count("fused segment:") == 3
+    assert plan.count("time-parallel scan") == 10 and "exact" not in plan
+    assert plan_of(g, 256, iir_mode=0).count("fused segment:") == 1     # the exact chain still fits one Program
