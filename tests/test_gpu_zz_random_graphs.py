@@ -65,3 +65,32 @@ def test_fifteen_reverbs_in_a_row_bit_exact(oracle_mod):
     assert eng.describe_plan().count("fused segment:") == 3
     assert_bit_exact(got[0], ref[0], "15 reverbs")
     assert np.count_nonzero(ref[0]) > 0
+
+
+def test_ten_one_pole_filters_in_scan_mode(oracle_mod):
+    """iir_mode = 1: four scan tables per Program, so the chain runs as three all-time-parallel segments (it used to fall
+    back to ten sequential recurrences).  Scan mode is the tolerance contract, not bit-exactness."""
+    from dsp_stuff_b200.engine import Engine
+    from tests.util import assert_audio_close, make_oracle
+
+    g = GraphSpec().node(100, "input").node(101, "output")
+    prev = 100
+    for i in range(10):
+        g.node(i, "low_pass" if i % 2 == 0 else "high_pass", ratio=0.5 + 0.04 * i)
+        g.link(prev, "out", i, "in")
+        prev = i
+    g.link(prev, "out", 101, "in")
+    C, n = 64, 128 * 40
+    x = S.noise(C, 2 * n)
+    e = Engine(C, block=128, max_samples=n, iir_mode=1)
+    g.apply(e)
+    plan = e.describe_plan()
+    o = make_oracle(oracle_mod, g, C)
+    for call in range(2):
+        got = e.process(x[:, call * n:(call + 1) * n])[0]
+        ref = o.process(x[:, call * n:(call + 1) * n])[0]
+        if "time-parallel scan" in plan and "exact" not in plan:
+            assert plan.count("fused segment:") == 3
+            assert_audio_close(got, ref, what=f"10 one-pole filters, scan mode, call {call}")
+        else:   # a filter failed the device probe: the whole segment is exact again
+            assert_bit_exact(got, ref, f"10 one-pole filters, exact fallback, call {call}")
