@@ -474,27 +474,16 @@ struct Lowerer {
         emit(d, b);
         return true;
     }
-    Value save_value(int ni, int port) {
-        Value v;
-        auto key = std::make_pair(ni, port);
-        const int us = use_step.count(key) ? use_step[key] : -1;
-        v.def_step = (int)steps.size();
-        if (us < 0) { v.where = Value::NONE; return v; }  // never used
-        if (us != v.def_step) {  // crosses a step boundary: global scratch
-            v.where = Value::GLOBAL;
-            v.bind_kind = 2;
-            v.bind_idx = n_scratch++;
-            Op o = mk(OP_STOREG);
-            o.buf = (uint8_t)buf_slot(2, v.bind_idx);
-            emit(o, "G" + std::to_string(o.buf) + " = acc                    ; scratch (crosses a step)");
-        } else {
-            v.where = Value::VREG;
-            v.id = new_vreg();
-            Op o = mk(OP_SAVEV);
-            o.vreg = (uint8_t)v.id;
-            emit(o, "v" + std::to_string(v.id) + " = acc");
-        }
-        return v;
+    // Scratch buffers ([C x max_samples] each) are reused: a buffer whose last reader ran in an EARLIER step than the one
+    // that defines the new value is free (steps are kernels in stream order; within one step a tile-by-tile writer could
+    // overtake a reader of the same buffer, hence strictly earlier).
+    std::vector<int> scratch_last_read;           // per scratch buffer: the last logical step that reads its current value
+    int alloc_scratch(int def_step, int last_use_step) {
+        for (size_t i = 0; i < scratch_last_read.size(); i++)
+            if (scratch_last_read[i] < def_step) { scratch_last_read[i] = last_use_step; return (int)i; }
+        scratch_last_read.push_back(last_use_step);
+        n_scratch = (int)scratch_last_read.size();
+        return n_scratch - 1;
     }
     int temp_save(const std::string& what) {
         int id = new_vreg();
@@ -785,7 +774,6 @@ int Lowerer::lower() {
         const size_t ops_before = ops.size();
         if (nd.type != T_FIR) cur_nodes.push_back(ni);   // dropped again below if the node emits nothing
         auto out_value = [&](int port) {
-            // like save_value but with the logical step numbering
             Value v;
             auto key = std::make_pair(ni, port);
             const int us = use_step.count(key) ? use_step[key] : -1;
@@ -793,7 +781,7 @@ int Lowerer::lower() {
             if (us != logical_step) {
                 v.where = Value::GLOBAL;
                 v.bind_kind = 2;
-                v.bind_idx = n_scratch++;
+                v.bind_idx = alloc_scratch(logical_step, us);
                 Op o = mk(OP_STOREG);
                 o.buf = (uint8_t)buf_slot(2, v.bind_idx);
                 emit(o, "G" + std::to_string(o.buf) + " = acc                    ; " + tag + " (used in a later step)");

@@ -7,7 +7,8 @@ lines of every segment) and check the DATAFLOW of what was lowered:
 
 * every shared-memory value read was written earlier in the same segment,
 * every scratch buffer / FIR output read was written by an earlier step (or earlier in the same segment, in which case the
-  read must not carry the one-tile-ahead prefetch flag),
+  read must not carry the one-tile-ahead prefetch flag); a scratch buffer is reused only by a step later than every reader
+  of its previous value,
 * every FIR step finds its input ring stored by the segment in front of it,
 * every output terminal is written exactly once,
 * every segment respects the Program limits.
@@ -61,8 +62,9 @@ def parse_plan(plan):
 
 def check_dataflow(plan, n_out_terms):
     written = set()          # scratchN / firU#id / firY#id written so far
+    last_read = {}           # scratchN -> index of the last step that read it (scratch buffers are reused)
     outs = {}
-    for st in parse_plan(plan):
+    for step_idx, st in enumerate(parse_plan(plan)):
         if st[0] == "fir":
             _, nid, term = st
             assert f"firU#{nid}" in written, f"fir#{nid} runs before its input was stored"
@@ -90,6 +92,7 @@ def check_dataflow(plan, n_out_terms):
                 assert not what.startswith("out") and not what.startswith("firU"), what
                 if not what.startswith("in"):
                     assert what in written, f"op {i} reads {what} before any step wrote it"
+                    last_read[what] = step_idx
                     if what in stored_here:
                         assert not op["pf"], f"op {i} prefetches {what}, which this very segment writes"
             if c == OP_STOREG:
@@ -99,7 +102,9 @@ def check_dataflow(plan, n_out_terms):
                     t = int(what[3:])
                     outs[t] = outs.get(t, 0) + 1
                 else:
-                    assert what not in written, f"{what} written twice"
+                    # a scratch buffer may be given a new value only by a LATER step than every reader of the old one
+                    assert what not in stored_here, f"{what} written twice in one segment"
+                    assert last_read.get(what, -1) < step_idx, f"{what} overwritten in the step that still reads its old value"
                     written.add(what)
                     stored_here.add(what)
     assert outs == {t: 1 for t in range(n_out_terms)}, outs
@@ -144,6 +149,8 @@ def test_long_chain_of_stateful_nodes_is_cut_at_the_state_limit():
     check_dataflow(plan, 1)
     assert plan.count("fused segment:") >= 4
     assert plan.count("DF1(") == 40
+    # one value crosses each cut; scratch buffers are reused once their reader's step is over: two buffers, ping-pong
+    assert len(set(re.findall(r"=scratch(\d+)", plan))) == 2
 
 
 def test_many_reverbs_are_cut_at_the_ring_limit():
